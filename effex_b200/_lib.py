@@ -1,0 +1,82 @@
+"""ctypes binding of libeffex_fx.so (C ABI declared in include/effex_fx.h).
+
+There is no fallback: if the shared library cannot be loaded this module
+raises, and every product entry point that needs the GPU fails with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeffex_fx.so")
+
+FX_OK = 0
+FX_ERR_INVALID = -1
+FX_ERR_CUDA = -2
+FX_ERR_UNSUPPORTED = -3
+FX_ERR_STATE = -4
+FX_FLAG_FORCE_GENERIC = 1
+
+
+class FxConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("ntaps", C.c_int32), ("nbins", C.c_int32),
+                ("dc_remove", C.c_int32), ("num_samp", C.c_int64), ("max_blocks", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+# name -> (restype, argtypes); mirrors include/effex_fx.h one to one
+_VP = C.c_void_p
+SIGNATURES = {
+    "fx_abi_version": (C.c_int, []),
+    "fx_device_count": (C.c_int, []),
+    "fx_create": (C.c_int, [C.POINTER(FxConfig), C.POINTER(_VP)]),
+    "fx_destroy": (C.c_int, [_VP]),
+    "fx_last_error": (C.c_char_p, [_VP]),
+    "fx_sync": (C.c_int, [_VP]),
+    "fx_uses_fused": (C.c_int, [_VP]),
+    "fx_set_taps": (C.c_int, [_VP, C.POINTER(C.c_double), C.c_size_t]),
+    "fx_set_rot": (C.c_int, [_VP, C.POINTER(C.c_double), C.c_size_t]),
+    "fx_process": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "fx_integrate": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "fx_process_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "fx_pfb_c64": (C.c_int, [_VP, _VP, _VP]),
+    "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),
+    "fx_lag_c64": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "fx_lag_u8": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "fx_dev_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
+    "fx_dev_free": (C.c_int, [_VP, _VP]),
+    "fx_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(_VP)]),
+    "fx_host_free_pinned": (C.c_int, [_VP]),
+    "fx_memcpy_h2d": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "fx_memcpy_d2h": (C.c_int, [_VP, _VP, _VP, C.c_size_t]),
+    "fx_memset": (C.c_int, [_VP, _VP, C.c_int, C.c_size_t]),
+    "fx_reset_counters": (C.c_int, [_VP]),
+    "fx_kernel_launches": (C.c_int64, [_VP]),
+    "fx_enable_timing": (C.c_int, [_VP, C.c_int]),
+    "fx_dominant_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "fx_stream": (_VP, [_VP]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libeffex_fx.so (building it first if nvcc is here and it is stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build          # raises if nvcc is missing
+        _build.build()
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:                       # pragma: no cover - environment specific
+        raise RuntimeError(
+            f"libeffex_fx.so could not be loaded ({e}); the FX hot path has no CPU fallback") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)                # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

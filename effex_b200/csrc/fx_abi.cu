@@ -1,0 +1,792 @@
+// fx_abi.cu -- C ABI of libeffex_fx.so (see include/effex_fx.h).
+// Host-side orchestration only: table building, segment planning, launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/effex_fx.h"
+#include "fx_common.cuh"
+#include "fx_fused4096.cuh"
+#include "fx_generic.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct fx_handle {
+    fx_config cfg{};
+    int P = 0;        // frames per block = num_samp / nbins
+    int logN = 0;
+    int num_sms = 148;
+    bool fused = false;
+    bool taps_set = false;
+    cudaStream_t stream = nullptr, stream_copy = nullptr;
+
+    // tables
+    float *d_taps_u8 = nullptr;   // [T][N] reversed within a branch, scaled by 1/127.5
+    float *d_taps_c = nullptr;    // [T][N] reversed, unscaled (complex64 input)
+    float4 *d_taps4 = nullptr;    // fused layout [N] (k = 0..3)
+    float2 *d_twA = nullptr, *d_twB = nullptr;
+    float2 *d_rot = nullptr;
+    bool rot_set = false;
+
+    // workspaces
+    unsigned long long *d_sums = nullptr;     // [max_blocks][2][2]
+    float2 *d_part_x = nullptr, *d_part_a = nullptr;
+    size_t part_cap = 0;                      // in segments
+    fx::fused4096::Segment *d_segs = nullptr;
+    size_t segs_cap = 0;
+    std::vector<fx::fused4096::Segment> h_segs;
+    long long planned_blocks = -1;
+    int planned_splits = 0;
+
+    float2 *d_g0 = nullptr, *d_g1 = nullptr, *d_gtmp = nullptr;   // generic-path frame buffers
+    size_t g_cap = 0;                                             // elements per buffer
+
+    float2 *d_lag_rows = nullptr, *d_lag_tmp = nullptr, *d_lag_acc = nullptr, *d_lag_acc_tmp = nullptr;
+    long long lagM = 0;
+    float *d_pval = nullptr;
+    long long *d_pidx = nullptr;
+    long long *d_lag_idx = nullptr;
+    float *d_lag_nb = nullptr;
+
+    // host-pipeline staging (fx_process_host)
+    uint8_t *d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    float *d_out_x[2] = {nullptr, nullptr}, *d_out_a0[2] = {nullptr, nullptr}, *d_out_a1[2] = {nullptr, nullptr};
+    int stage_blocks = 0;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    std::string err;
+    long long launches = 0;
+    bool timing = false;
+    std::vector<EventPair> evs;
+    double timed_ms = 0.0;
+    long long timed_launches = 0;
+};
+
+namespace {
+
+int fail(fx_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define FX_CUDA(h, expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail((h), FX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+#define FX_LAUNCH_CHECK(h, name)                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                     \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail((h), FX_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e_)); \
+        (h)->launches++;                                                                         \
+    } while (0)
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
+
+int begin_timed(fx_handle *h, EventPair &ep) {
+    if (!h->timing) return FX_OK;
+    FX_CUDA(h, cudaEventCreate(&ep.a));
+    FX_CUDA(h, cudaEventCreate(&ep.b));
+    FX_CUDA(h, cudaEventRecord(ep.a, h->stream));
+    return FX_OK;
+}
+int end_timed(fx_handle *h, EventPair &ep) {
+    if (!h->timing) return FX_OK;
+    FX_CUDA(h, cudaEventRecord(ep.b, h->stream));
+    h->evs.push_back(ep);
+    return FX_OK;
+}
+int drain_timed(fx_handle *h) {
+    for (auto &ep : h->evs) {
+        FX_CUDA(h, cudaEventSynchronize(ep.b));
+        float ms = 0.f;
+        FX_CUDA(h, cudaEventElapsedTime(&ms, ep.a, ep.b));
+        h->timed_ms += ms;
+        h->timed_launches++;
+        cudaEventDestroy(ep.a);
+        cudaEventDestroy(ep.b);
+    }
+    h->evs.clear();
+    return FX_OK;
+}
+
+// ---- per-block byte sums for both channels --------------------------------
+int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
+    const long long S = h->cfg.num_samp;
+    FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, h->stream));
+    long long chunks = (S + 256 * 32 - 1) / (256 * 32);
+    if (chunks > 64) chunks = 64;
+    if (chunks < 1) chunks = 1;
+    for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
+        const long long nb = std::min<long long>(65535, n_blocks - b0);
+        dim3 grid((unsigned)chunks, (unsigned)nb);
+        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, h->d_sums + 4 * b0, 4);
+        FX_LAUNCH_CHECK(h, "block_sums");
+        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq1 + 2 * S * b0, S, h->d_sums + 4 * b0 + 2, 4);
+        FX_LAUNCH_CHECK(h, "block_sums");
+    }
+    return FX_OK;
+}
+
+int ensure_parts(fx_handle *h, size_t n_segs) {
+    if (n_segs <= h->part_cap) return FX_OK;
+    if (h->d_part_x) cudaFree(h->d_part_x);
+    if (h->d_part_a) cudaFree(h->d_part_a);
+    h->d_part_x = h->d_part_a = nullptr;
+    h->part_cap = 0;
+    const size_t bytes = n_segs * (size_t)h->cfg.nbins * sizeof(float2);
+    FX_CUDA(h, cudaMalloc(&h->d_part_x, bytes));
+    FX_CUDA(h, cudaMalloc(&h->d_part_a, bytes));
+    h->part_cap = n_segs;
+    return FX_OK;
+}
+
+// Choose how many segments each block is cut into so that the persistent grid
+// (one CTA per SM) finishes in the fewest frame-times.
+int plan_segments(fx_handle *h, long long n_blocks) {
+    if (h->planned_blocks == n_blocks) return FX_OK;
+    const int P = h->P;
+    int best_s = 1;
+    double best_cost = 1e300;
+    for (int s = 1; s <= P; s *= 2) {
+        const int len = (P + s - 1) / s;
+        if (s > 1 && len < 2) break;
+        const long long nseg = n_blocks * ((P + len - 1) / len);
+        const long long waves = (nseg + h->num_sms - 1) / h->num_sms;
+        const double cost = (double)waves * (len + 0.6);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
+    }
+    const int len = (P + best_s - 1) / best_s;
+    const int splits = (P + len - 1) / len;
+    h->h_segs.clear();
+    h->h_segs.reserve((size_t)n_blocks * splits);
+    for (long long b = 0; b < n_blocks; ++b)
+        for (int s = 0; s < splits; ++s) {
+            fx::fused4096::Segment sg;
+            sg.block = (int)b;
+            sg.f0 = s * len;
+            sg.nf = std::min(len, P - s * len);
+            sg.pad = 0;
+            h->h_segs.push_back(sg);
+        }
+    if (h->h_segs.size() > h->segs_cap) {
+        if (h->d_segs) cudaFree(h->d_segs);
+        h->d_segs = nullptr;
+        h->segs_cap = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_segs, h->h_segs.size() * sizeof(fx::fused4096::Segment)));
+        h->segs_cap = h->h_segs.size();
+    }
+    // synchronous copy: h_segs may be rebuilt by the next call before an async copy is consumed
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    FX_CUDA(h, cudaMemcpy(h->d_segs, h->h_segs.data(), h->h_segs.size() * sizeof(fx::fused4096::Segment),
+                          cudaMemcpyHostToDevice));
+    h->planned_blocks = n_blocks;
+    h->planned_splits = splits;
+    int rc = ensure_parts(h, h->h_segs.size());
+    return rc;
+}
+
+// fused path: sums -> fused kernel -> partial sums [n_blocks*splits][N]
+int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
+    int rc = launch_sums(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    rc = plan_segments(h, n_blocks);
+    if (rc) return rc;
+    fx::fused4096::Params prm;
+    prm.iq0 = d_iq0; prm.iq1 = d_iq1; prm.sums = h->d_sums;
+    prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB;
+    prm.segs = h->d_segs; prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
+    prm.S = h->cfg.num_samp; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
+    const int grid = std::min<int>(prm.n_segs, h->num_sms);
+    EventPair ep{};
+    rc = begin_timed(h, ep);
+    if (rc) return rc;
+    fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
+    FX_LAUNCH_CHECK(h, "fused4096");
+    return end_timed(h, ep);
+}
+
+int ensure_generic(fx_handle *h, size_t elems) {
+    if (elems <= h->g_cap) return FX_OK;
+    for (float2 **p : {&h->d_g0, &h->d_g1, &h->d_gtmp}) { if (*p) cudaFree(*p); *p = nullptr; }
+    h->g_cap = 0;
+    FX_CUDA(h, cudaMalloc(&h->d_g0, elems * sizeof(float2)));
+    FX_CUDA(h, cudaMalloc(&h->d_g1, elems * sizeof(float2)));
+    FX_CUDA(h, cudaMalloc(&h->d_gtmp, elems * sizeof(float2)));
+    h->g_cap = elems;
+    return FX_OK;
+}
+
+__global__ void phase_post_kernel(float2 *x, int N, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i & (N - 1));
+    float sn, cs;
+    sincospif(-2.f * (float)c / (float)N, &sn, &cs);
+    const float2 v = x[i];
+    x[i] = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+}
+
+// batched FFT of `rows` rows of length N held in buf; tmp is scratch of the same size.
+// Result is left in buf.
+int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, int inverse, int phase_post,
+                bool timed) {
+    const int logN = ilog2(N);
+    EventPair ep{};
+    int rc = timed ? begin_timed(h, ep) : FX_OK;
+    if (rc) return rc;
+    if (N <= 4096) {
+        const int threads = std::max(32, std::min(512, N / 2));
+        const size_t smem = 2 * (size_t)N * sizeof(float2);
+        for (long long r0 = 0; r0 < rows; r0 += (1ll << 30)) {
+            const long long nr = std::min<long long>(1ll << 30, rows - r0);
+            fx::generic::fft_rows_kernel<<<(unsigned)nr, threads, smem, h->stream>>>(buf + r0 * N, buf + r0 * N, N, logN,
+                                                                                   inverse, phase_post);
+            FX_LAUNCH_CHECK(h, "fft_rows");
+        }
+    } else {
+        float2 *src = buf, *dst = tmp;
+        for (int s = 0; s < logN; ++s) {
+            dim3 grid((unsigned)((N / 2 + 255) / 256), (unsigned)rows);
+            fx::generic::stockham_pass_kernel<<<grid, 256, 0, h->stream>>>(src, dst, N, 1ll << s, inverse);
+            FX_LAUNCH_CHECK(h, "stockham_pass");
+            std::swap(src, dst);
+        }
+        if (src != buf)
+            FX_CUDA(h, cudaMemcpyAsync(buf, src, sizeof(float2) * (size_t)N * rows, cudaMemcpyDeviceToDevice, h->stream));
+        if (phase_post) {
+            const long long total = (long long)N * rows;
+            phase_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(buf, N, total);
+            FX_LAUNCH_CHECK(h, "phase_post");
+        }
+    }
+    return timed ? end_timed(h, ep) : FX_OK;
+}
+
+// generic path for a chunk of blocks: FIR -> FFT -> X-engine into parts[b0 .. b0+nb)
+int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long b0, long long nb) {
+    const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
+    const long long S = h->cfg.num_samp;
+    dim3 grid((N + 255) / 256, P, (unsigned)nb);
+    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
+                                                                  h->d_sums + 4 * b0, 4, h->cfg.dc_remove, h->d_g0);
+    FX_LAUNCH_CHECK(h, "pfb_fir");
+    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq1 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
+                                                                  h->d_sums + 4 * b0 + 2, 4, h->cfg.dc_remove, h->d_g1);
+    FX_LAUNCH_CHECK(h, "pfb_fir");
+    int rc = fft_batched(h, h->d_g0, h->d_gtmp, N, nb * P, 0, 0, true);
+    if (rc) return rc;
+    rc = fft_batched(h, h->d_g1, h->d_gtmp, N, nb * P, 0, 0, true);
+    if (rc) return rc;
+    dim3 gx((N + 255) / 256, (unsigned)nb);
+    fx::generic::xengine_kernel<<<gx, 256, 0, h->stream>>>(h->d_g0, h->d_g1, N, P, h->d_part_x + b0 * N,
+                                                         h->d_part_a + b0 * N);
+    FX_LAUNCH_CHECK(h, "xengine");
+    return FX_OK;
+}
+
+long long generic_chunk_blocks(const fx_handle *h) {
+    const size_t per_block = (size_t)h->P * h->cfg.nbins;
+    long long c = (long long)((size_t(1) << 25) / std::max<size_t>(per_block, 1));   // <= 256 MiB per buffer
+    if (c < 1) c = 1;
+    if (c > 16384) c = 16384;
+    return c;
+}
+
+int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
+    int rc = launch_sums(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    rc = ensure_parts(h, (size_t)n_blocks);
+    if (rc) return rc;
+    const long long chunk = std::min<long long>(generic_chunk_blocks(h), n_blocks);
+    rc = ensure_generic(h, (size_t)chunk * h->P * h->cfg.nbins);
+    if (rc) return rc;
+    for (long long b0 = 0; b0 < n_blocks; b0 += chunk) {
+        rc = run_generic_chunk(h, d_iq0, d_iq1, b0, std::min(chunk, n_blocks - b0));
+        if (rc) return rc;
+    }
+    h->planned_splits = 1;
+    h->planned_blocks = -1;
+    return FX_OK;
+}
+
+int check_process_args(fx_handle *h, const void *a, const void *b, long long n_blocks) {
+    if (!h) return FX_ERR_INVALID;
+    if (!h->taps_set) return fail(h, FX_ERR_STATE, "fx_set_taps must be called first");
+    if (!a || !b) return fail(h, FX_ERR_INVALID, "null input pointer");
+    if (n_blocks < 1 || n_blocks > h->cfg.max_blocks)
+        return fail(h, FX_ERR_INVALID, "n_blocks must be in [1, max_blocks]");
+    return FX_OK;
+}
+
+bool fused_ok_for(const fx_handle *h, const void *a, const void *b) {
+    return h->fused && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
+    if (fused_ok_for(h, d_iq0, d_iq1)) return run_fused(h, d_iq0, d_iq1, n_blocks);
+    return run_generic(h, d_iq0, d_iq1, n_blocks);
+}
+
+int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
+                   float *d_auto0, float *d_auto1) {
+    int rc = run_parts(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    const int N = h->cfg.nbins;
+    dim3 grid((N + 255) / 256, 1);
+    for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
+        const long long nb = std::min<long long>(65535, n_blocks - b0);
+        grid.y = (unsigned)nb;
+        fx::generic::finalize_rows_kernel<<<grid, 256, 0, h->stream>>>(
+            h->d_part_x + b0 * h->planned_splits * N, h->d_part_a + b0 * h->planned_splits * N, N, h->planned_splits,
+            1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec) + b0 * N,
+            d_auto0 ? d_auto0 + b0 * N : nullptr, d_auto1 ? d_auto1 + b0 * N : nullptr);
+        FX_LAUNCH_CHECK(h, "finalize_rows");
+    }
+    return FX_OK;
+}
+
+int ensure_lag(fx_handle *h, long long M) {
+    if (M == h->lagM) return FX_OK;
+    for (float2 **p : {&h->d_lag_rows, &h->d_lag_tmp, &h->d_lag_acc, &h->d_lag_acc_tmp}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    h->lagM = 0;
+    FX_CUDA(h, cudaMalloc(&h->d_lag_rows, sizeof(float2) * 2 * M));
+    FX_CUDA(h, cudaMalloc(&h->d_lag_tmp, sizeof(float2) * 2 * M));
+    FX_CUDA(h, cudaMalloc(&h->d_lag_acc, sizeof(float2) * M));
+    FX_CUDA(h, cudaMalloc(&h->d_lag_acc_tmp, sizeof(float2) * M));
+    if (!h->d_pval) {
+        FX_CUDA(h, cudaMalloc(&h->d_pval, sizeof(float) * 1024));
+        FX_CUDA(h, cudaMalloc(&h->d_pidx, sizeof(long long) * 1024));
+        FX_CUDA(h, cudaMalloc(&h->d_lag_idx, sizeof(long long)));
+        FX_CUDA(h, cudaMalloc(&h->d_lag_nb, sizeof(float) * 4));
+    }
+    h->lagM = M;
+    return FX_OK;
+}
+
+// in-place (result in buf) global-memory FFT of `rows` rows of length M
+int fft_global(fx_handle *h, float2 *buf, float2 *tmp, long long M, int rows, int inverse) {
+    const int logM = ilog2(M);
+    float2 *src = buf, *dst = tmp;
+    for (int s = 0; s < logM; ++s) {
+        dim3 grid((unsigned)((M / 2 + 255) / 256), (unsigned)rows);
+        fx::generic::stockham_pass_kernel<<<grid, 256, 0, h->stream>>>(src, dst, M, 1ll << s, inverse);
+        FX_LAUNCH_CHECK(h, "stockham_pass");
+        std::swap(src, dst);
+    }
+    if (src != buf)
+        FX_CUDA(h, cudaMemcpyAsync(buf, src, sizeof(float2) * (size_t)M * rows, cudaMemcpyDeviceToDevice, h->stream));
+    return FX_OK;
+}
+
+template <bool U8>
+int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, int64_t *imax, float nbhd[3]) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d0 || !d1 || !imax || !nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
+    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const long long n = h->cfg.num_samp;
+    long long M = 2;
+    while (M < 2 * n) M <<= 1;
+    int rc = ensure_lag(h, M);
+    if (rc) return rc;
+    if (U8) {
+        if (n_blocks > h->cfg.max_blocks) return fail(h, FX_ERR_INVALID, "n_blocks exceeds max_blocks");
+        rc = launch_sums(h, (const uint8_t *)d0, (const uint8_t *)d1, n_blocks);
+        if (rc) return rc;
+    }
+    for (long long b = 0; b < n_blocks; ++b) {
+        dim3 grid((unsigned)((M + 255) / 256), 2);
+        fx::generic::lag_load_kernel<U8><<<grid, 256, 0, h->stream>>>(d0, d1, n, M, b, h->d_sums, h->cfg.dc_remove,
+                                                                     h->d_lag_rows);
+        FX_LAUNCH_CHECK(h, "lag_load");
+        rc = fft_global(h, h->d_lag_rows, h->d_lag_tmp, M, 2, 0);
+        if (rc) return rc;
+        fx::generic::lag_accum_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(h->d_lag_rows, M, b == 0,
+                                                                                        h->d_lag_acc);
+        FX_LAUNCH_CHECK(h, "lag_accum");
+    }
+    rc = fft_global(h, h->d_lag_acc, h->d_lag_acc_tmp, M, 1, 1);
+    if (rc) return rc;
+    const int nparts = (int)std::min<long long>(1024, (2 * n + 255) / 256);
+    fx::generic::lag_argmax_stage1<<<nparts, 256, 0, h->stream>>>(h->d_lag_acc, n, M, h->d_pval, h->d_pidx);
+    FX_LAUNCH_CHECK(h, "lag_argmax_stage1");
+    const float scale = (float)(1.0 / ((double)M * 2.0 * (double)n));
+    fx::generic::lag_argmax_stage2<<<1, 256, 0, h->stream>>>(h->d_lag_acc, n, M, h->d_pval, h->d_pidx, nparts, scale,
+                                                            h->d_lag_idx, h->d_lag_nb);
+    FX_LAUNCH_CHECK(h, "lag_argmax_stage2");
+    long long idx = 0;
+    float nb[3];
+    FX_CUDA(h, cudaMemcpyAsync(&idx, h->d_lag_idx, sizeof(idx), cudaMemcpyDeviceToHost, h->stream));
+    FX_CUDA(h, cudaMemcpyAsync(nb, h->d_lag_nb, sizeof(nb), cudaMemcpyDeviceToHost, h->stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *imax = idx;
+    nbhd[0] = nb[0]; nbhd[1] = nb[1]; nbhd[2] = nb[2];
+    return FX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fx_abi_version(void) { return FX_ABI_VERSION; }
+
+int fx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int fx_create(const fx_config *cfg, fx_handle **out) {
+    if (!cfg || !out) return fail(nullptr, FX_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->ntaps < 1) return fail(nullptr, FX_ERR_INVALID, "ntaps must be >= 1");
+    if (cfg->ntaps > fx::kMaxTaps)
+        return fail(nullptr, FX_ERR_UNSUPPORTED, "ntaps > 32 is not supported (cuSignal channelize_poly has the same cap)");
+    if (!is_pow2(cfg->nbins) || cfg->nbins < 8 || cfg->nbins > 65536)
+        return fail(nullptr, FX_ERR_UNSUPPORTED, "nbins must be a power of two in [8, 65536]");
+    if (cfg->num_samp < 1) return fail(nullptr, FX_ERR_INVALID, "num_samp must be >= 1");
+    if (cfg->num_samp / cfg->nbins < 1)
+        return fail(nullptr, FX_ERR_INVALID, "there must be at least one frame of nbins samples per block");
+    if (cfg->max_blocks < 1) return fail(nullptr, FX_ERR_INVALID, "max_blocks must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, FX_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                              " (libeffex_fx has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, FX_ERR_INVALID, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, FX_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, FX_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, FX_ERR_UNSUPPORTED, "libeffex_fx is built for sm_100a (B200) only");
+
+    fx_handle *h = new fx_handle();
+    h->cfg = *cfg;
+    h->P = (int)(cfg->num_samp / cfg->nbins);
+    h->logN = ilog2(cfg->nbins);
+    h->num_sms = prop.multiProcessorCount;
+    h->fused = cfg->nbins == fx::fused4096::N && cfg->ntaps == fx::fused4096::T && (cfg->num_samp % 8) == 0 &&
+               !(cfg->flags & FX_FLAG_FORCE_GENERIC);
+    auto bail = [&](const std::string &m) { g_create_error = m; fx_destroy(h); return FX_ERR_CUDA; };
+#define CREATE_CUDA(expr)                                                        \
+    do {                                                                         \
+        cudaError_t e2_ = (expr);                                                \
+        if (e2_ != cudaSuccess) return bail(std::string(#expr) + ": " + cudaGetErrorString(e2_)); \
+    } while (0)
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+    const size_t TN = (size_t)cfg->ntaps * cfg->nbins;
+    CREATE_CUDA(cudaMalloc(&h->d_taps_u8, TN * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&h->d_taps_c, TN * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&h->d_rot, (size_t)cfg->nbins * sizeof(float2)));
+    CREATE_CUDA(cudaMalloc(&h->d_sums, sizeof(unsigned long long) * 4 * (size_t)cfg->max_blocks));
+    CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     2 * 4096 * (int)sizeof(float2)));
+    if (h->fused) {
+        CREATE_CUDA(cudaMalloc(&h->d_taps4, fx::fused4096::N * sizeof(float4)));
+        CREATE_CUDA(cudaMalloc(&h->d_twA, 16 * 256 * sizeof(float2)));
+        CREATE_CUDA(cudaMalloc(&h->d_twB, 16 * 16 * sizeof(float2)));
+        std::vector<float2> twA(16 * 256), twB(16 * 16);
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int t = 0; t < 256; ++t) {
+                const double a = -2.0 * M_PI * (double)((k1 * t) % 4096) / 4096.0;
+                twA[k1 * 256 + t] = make_float2((float)cos(a), (float)sin(a));
+            }
+        for (int k2 = 0; k2 < 16; ++k2)
+            for (int n3 = 0; n3 < 16; ++n3) {
+                const double a = -2.0 * M_PI * (double)((k2 * n3) % 256) / 256.0;
+                twB[k2 * 16 + n3] = make_float2((float)cos(a), (float)sin(a));
+            }
+        CREATE_CUDA(cudaMemcpy(h->d_twA, twA.data(), twA.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(h->d_twB, twB.data(), twB.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(fx::fused4096::Smem)));
+    }
+#undef CREATE_CUDA
+    *out = h;
+    return FX_OK;
+}
+
+int fx_destroy(fx_handle *h) {
+    if (!h) return FX_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
+    for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+    void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums, h->d_part_x,
+                    h->d_part_a, h->d_segs, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
+                    h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
+                    h->d_out_a1[0], h->d_out_a1[1]};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
+    delete h;
+    return FX_OK;
+}
+
+const char *fx_last_error(const fx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fx_sync(fx_handle *h) {
+    if (!h) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream_copy));
+    return FX_OK;
+}
+
+int fx_uses_fused(const fx_handle *h) { return h && h->fused ? 1 : 0; }
+
+int fx_set_taps(fx_handle *h, const double *taps, size_t n) {
+    if (!h) return FX_ERR_INVALID;
+    const int N = h->cfg.nbins, T = h->cfg.ntaps;
+    if (!taps || n != (size_t)N * T) return fail(h, FX_ERR_INVALID, "taps must hold ntaps*nbins float64 values");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    std::vector<float> tu((size_t)N * T), tc((size_t)N * T);
+    for (int k = 0; k < T; ++k)
+        for (int p = 0; p < N; ++p) {
+            const double v = taps[(size_t)k * N + (N - 1 - p)];   // h[kN + N-1-p]  
+            tu[(size_t)k * N + p] = (float)(v / 127.5);
+            tc[(size_t)k * N + p] = (float)v;
+        }
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    FX_CUDA(h, cudaMemcpy(h->d_taps_u8, tu.data(), tu.size() * sizeof(float), cudaMemcpyHostToDevice));
+    FX_CUDA(h, cudaMemcpy(h->d_taps_c, tc.data(), tc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->fused) {
+        std::vector<float4> t4(N);
+        for (int p = 0; p < N; ++p)
+            t4[p] = make_float4(tu[p], tu[(size_t)N + p], tu[(size_t)2 * N + p], tu[(size_t)3 * N + p]);
+        FX_CUDA(h, cudaMemcpy(h->d_taps4, t4.data(), t4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    h->taps_set = true;
+    return FX_OK;
+}
+
+int fx_set_rot(fx_handle *h, const double *rot, size_t nbins) {
+    if (!h) return FX_ERR_INVALID;
+    if (!rot) { h->rot_set = false; return FX_OK; }
+    if (nbins != (size_t)h->cfg.nbins) return fail(h, FX_ERR_INVALID, "rot must hold nbins (re,im) pairs");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    std::vector<float2> r(nbins);
+    for (size_t c = 0; c < nbins; ++c) r[c] = make_float2((float)rot[2 * c], (float)rot[2 * c + 1]);
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    FX_CUDA(h, cudaMemcpy(h->d_rot, r.data(), r.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    h->rot_set = true;
+    return FX_OK;
+}
+
+int fx_process(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, float *d_xspec,
+               float *d_auto0, float *d_auto1) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!d_xspec) return fail(h, FX_ERR_INVALID, "null output pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1);
+}
+
+int fx_integrate(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, double *d_acc_x,
+                 double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!d_acc_x || !d_acc_a0 || !d_acc_a1) return fail(h, FX_ERR_INVALID, "null accumulator pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    rc = run_parts(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    const int N = h->cfg.nbins;
+    const int n_segs = (int)(n_blocks * h->planned_splits);
+    fx::generic::integrate_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(
+        h->d_part_x, h->d_part_a, N, n_segs, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+    FX_LAUNCH_CHECK(h, "integrate");
+    return FX_OK;
+}
+
+int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,
+                    float *h_auto0, float *h_auto1) {
+    if (!h) return FX_ERR_INVALID;
+    if (!h->taps_set) return fail(h, FX_ERR_STATE, "fx_set_taps must be called first");
+    if (!h_iq0 || !h_iq1 || !h_xspec) return fail(h, FX_ERR_INVALID, "null pointer");
+    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const long long S = h->cfg.num_samp;
+    const int N = h->cfg.nbins;
+    const size_t blk_bytes = 2 * (size_t)S;
+    // chunk: about 32 MiB of raw bytes per channel, at most max_blocks
+    long long chunk = std::max<long long>(1, (long long)((size_t(32) << 20) / blk_bytes));
+    chunk = std::min<long long>(chunk, h->cfg.max_blocks);
+    chunk = std::min<long long>(chunk, n_blocks);
+    if (h->stage_blocks < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            for (int c = 0; c < 2; ++c) { if (h->d_in[i][c]) cudaFree(h->d_in[i][c]); h->d_in[i][c] = nullptr; }
+            for (float **p : {&h->d_out_x[i], &h->d_out_a0[i], &h->d_out_a1[i]}) { if (*p) cudaFree(*p); *p = nullptr; }
+        }
+        h->stage_blocks = 0;
+        for (int i = 0; i < 2; ++i) {
+            for (int c = 0; c < 2; ++c) FX_CUDA(h, cudaMalloc(&h->d_in[i][c], blk_bytes * chunk));
+            FX_CUDA(h, cudaMalloc(&h->d_out_x[i], sizeof(float2) * (size_t)N * chunk));
+            FX_CUDA(h, cudaMalloc(&h->d_out_a0[i], sizeof(float) * (size_t)N * chunk));
+            FX_CUDA(h, cudaMalloc(&h->d_out_a1[i], sizeof(float) * (size_t)N * chunk));
+            if (!h->ev_in[i]) FX_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            if (!h->ev_done[i]) FX_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+        h->stage_blocks = (int)chunk;
+    }
+    int it = 0;
+    for (long long b0 = 0; b0 < n_blocks; b0 += chunk, ++it) {
+        const long long nb = std::min(chunk, n_blocks - b0);
+        const int s = it & 1;
+        if (it >= 2) FX_CUDA(h, cudaStreamWaitEvent(h->stream_copy, h->ev_done[s], 0));
+        FX_CUDA(h, cudaMemcpyAsync(h->d_in[s][0], h_iq0 + blk_bytes * b0, blk_bytes * nb, cudaMemcpyHostToDevice,
+                                   h->stream_copy));
+        FX_CUDA(h, cudaMemcpyAsync(h->d_in[s][1], h_iq1 + blk_bytes * b0, blk_bytes * nb, cudaMemcpyHostToDevice,
+                                   h->stream_copy));
+        FX_CUDA(h, cudaEventRecord(h->ev_in[s], h->stream_copy));
+        FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+        int rc = process_device(h, h->d_in[s][0], h->d_in[s][1], nb, h->d_out_x[s], h_auto0 ? h->d_out_a0[s] : nullptr,
+                                h_auto1 ? h->d_out_a1[s] : nullptr);
+        if (rc) return rc;
+        FX_CUDA(h, cudaMemcpyAsync(h_xspec + 2 * (size_t)N * b0, h->d_out_x[s], sizeof(float2) * (size_t)N * nb,
+                                   cudaMemcpyDeviceToHost, h->stream));
+        if (h_auto0)
+            FX_CUDA(h, cudaMemcpyAsync(h_auto0 + (size_t)N * b0, h->d_out_a0[s], sizeof(float) * (size_t)N * nb,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        if (h_auto1)
+            FX_CUDA(h, cudaMemcpyAsync(h_auto1 + (size_t)N * b0, h->d_out_a1[s], sizeof(float) * (size_t)N * nb,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        FX_CUDA(h, cudaEventRecord(h->ev_done[s], h->stream));
+    }
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FX_OK;
+}
+
+int fx_pfb_c64(fx_handle *h, const float *d_x, float *d_frames) {
+    if (!h) return FX_ERR_INVALID;
+    if (!h->taps_set) return fail(h, FX_ERR_STATE, "fx_set_taps must be called first");
+    if (!d_x || !d_frames) return fail(h, FX_ERR_INVALID, "null pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
+    int rc = ensure_generic(h, (size_t)P * N);
+    if (rc) return rc;
+    dim3 grid((N + 255) / 256, P, 1);
+    float2 *out = reinterpret_cast<float2 *>(d_frames);
+    fx::generic::pfb_fir_kernel<false><<<grid, 256, 0, h->stream>>>(d_x, h->cfg.num_samp, N, T, P, h->d_taps_c,
+                                                                   nullptr, 0, 0, out);
+    FX_LAUNCH_CHECK(h, "pfb_fir");
+    return fft_batched(h, out, h->d_gtmp, N, P, 0, 1, true);
+}
+
+int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames) {
+    if (!h) return FX_ERR_INVALID;
+    if (!h->taps_set) return fail(h, FX_ERR_STATE, "fx_set_taps must be called first");
+    if (!d_iq || !d_frames) return fail(h, FX_ERR_INVALID, "null pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
+    int rc = ensure_generic(h, (size_t)P * N);
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4, h->stream));
+    long long chunks = std::min<long long>(64, std::max<long long>(1, h->cfg.num_samp / 8192));
+    fx::generic::block_sums_kernel<<<dim3((unsigned)chunks, 1), 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, h->d_sums, 4);
+    FX_LAUNCH_CHECK(h, "block_sums");
+    dim3 grid((N + 255) / 256, P, 1);
+    float2 *out = reinterpret_cast<float2 *>(d_frames);
+    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, N, T, P, h->d_taps_u8,
+                                                                  h->d_sums, 4, h->cfg.dc_remove, out);
+    FX_LAUNCH_CHECK(h, "pfb_fir");
+    return fft_batched(h, out, h->d_gtmp, N, P, 0, 1, true);
+}
+
+int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blocks, int64_t *imax, float nbhd[3]) {
+    return lag_impl<false>(h, d_x0, d_x1, n_blocks, imax, nbhd);
+}
+int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, int64_t *imax,
+              float nbhd[3]) {
+    return lag_impl<true>(h, d_iq0, d_iq1, n_blocks, imax, nbhd);
+}
+
+int fx_dev_alloc(fx_handle *h, size_t bytes, void **d_ptr) {
+    if (!h || !d_ptr) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaMalloc(d_ptr, bytes));
+    return FX_OK;
+}
+int fx_dev_free(fx_handle *h, void *d_ptr) {
+    if (!h) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaFree(d_ptr));
+    return FX_OK;
+}
+int fx_host_alloc_pinned(size_t bytes, void **h_ptr) {
+    if (!h_ptr) return FX_ERR_INVALID;
+    return cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? FX_OK : FX_ERR_CUDA;
+}
+int fx_host_free_pinned(void *h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? FX_OK : FX_ERR_CUDA; }
+int fx_memcpy_h2d(fx_handle *h, void *d_dst, const void *h_src, size_t bytes) {
+    if (!h) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, h->stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FX_OK;
+}
+int fx_memcpy_d2h(fx_handle *h, void *h_dst, const void *d_src, size_t bytes) {
+    if (!h) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FX_OK;
+}
+int fx_memset(fx_handle *h, void *d_ptr, int value, size_t bytes) {
+    if (!h) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaMemsetAsync(d_ptr, value, bytes, h->stream));
+    return FX_OK;
+}
+
+int fx_reset_counters(fx_handle *h) {
+    if (!h) return FX_ERR_INVALID;
+    int rc = drain_timed(h);
+    h->launches = 0;
+    h->timed_ms = 0.0;
+    h->timed_launches = 0;
+    return rc;
+}
+int64_t fx_kernel_launches(const fx_handle *h) { return h ? h->launches : 0; }
+int fx_enable_timing(fx_handle *h, int on) {
+    if (!h) return FX_ERR_INVALID;
+    h->timing = on != 0;
+    return FX_OK;
+}
+int fx_dominant_kernel_time(fx_handle *h, double *ms_total, int64_t *launches) {
+    if (!h) return FX_ERR_INVALID;
+    int rc = drain_timed(h);
+    if (rc) return rc;
+    if (ms_total) *ms_total = h->timed_ms;
+    if (launches) *launches = h->timed_launches;
+    return FX_OK;
+}
+void *fx_stream(fx_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+}  // extern "C"

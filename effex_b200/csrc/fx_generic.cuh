@@ -1,0 +1,356 @@
+// fx_generic.cuh -- shape-generic kernels: block sums, PFB FIR, batched FFT,
+// X-engine, finalize/integrate, and the delay-calibration lag search.
+// They serve every (ntaps <= 32, nbins = 2^k) the fused kernels do not cover,
+// expose the pieces the reference's tests call on their own, and cross-check
+// the fused path on the device.
+#pragma once
+#include "fx_common.cuh"
+
+namespace fx {
+namespace generic {
+
+// ---------------------------------------------------------------------------
+// Exact per-block byte sums (for the DC removal of effex.py:394-395).
+// sums[b][0] += sum of I bytes, sums[b][1] += sum of Q bytes (stride: sums + b*stride).
+// grid = (chunks, n_blocks).  HBM-bound streaming read.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restrict__ iq, long long S,
+                                                         unsigned long long *__restrict__ sums, int stride) {
+    const int b = blockIdx.y;
+    const uint8_t *base = iq + 2ll * S * b;
+    unsigned int si = 0, sq = 0;
+    const long long nbytes = 2ll * S;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    const long long nvec = aligned ? nbytes / 16 : 0;
+    const uint4 *v = reinterpret_cast<const uint4 *>(base);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(v + i);
+        si = __dp4a(q.x, 0x00010001u, si); sq = __dp4a(q.x, 0x01000100u, sq);
+        si = __dp4a(q.y, 0x00010001u, si); sq = __dp4a(q.y, 0x01000100u, sq);
+        si = __dp4a(q.z, 0x00010001u, si); sq = __dp4a(q.z, 0x01000100u, sq);
+        si = __dp4a(q.w, 0x00010001u, si); sq = __dp4a(q.w, 0x01000100u, sq);
+    }
+    // tail (or everything, when the block is not 16-byte aligned): one sample per thread
+    for (long long s = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; s < S;
+         s += (long long)gridDim.x * blockDim.x) {
+        si += base[2 * s];
+        sq += base[2 * s + 1];
+    }
+    unsigned long long wi = si, wq = sq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wi += __shfl_xor_sync(0xffffffffu, wi, o);
+        wq += __shfl_xor_sync(0xffffffffu, wq, o);
+    }
+    __shared__ unsigned long long red[2][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = wi; red[1][warp] = wq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
+        atomicAdd(sums + (long long)b * stride, a);
+        atomicAdd(sums + (long long)b * stride + 1, c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// PFB FIR, any T <= 32, any N.   w[b][i][p] = sum_{k<=min(i,T-1)} taps[k][p] * x[(i-k)N + p]
+// taps[k][p] = h[kN + N-1-p] (already reversed; the u8 variant is pre-scaled by 1/127.5)
+// grid = (ceil(N/256), P, n_blocks)
+// ---------------------------------------------------------------------------
+template <bool U8>
+__global__ void __launch_bounds__(256) pfb_fir_kernel(const void *__restrict__ in, long long S, int N, int T, int P,
+                                                      const float *__restrict__ taps,
+                                                      const unsigned long long *__restrict__ sums, int sum_stride,
+                                                      int dc_remove, float2 *__restrict__ w) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    if (p >= N) return;
+    float mi = 0.f, mq = 0.f;
+    if (U8) {
+        if (dc_remove) {
+            mi = (float)((double)sums[(long long)b * sum_stride] / (double)S);
+            mq = (float)((double)sums[(long long)b * sum_stride + 1] / (double)S);
+        } else {
+            mi = mq = 127.5f;
+        }
+    }
+    float ar = 0.f, ai = 0.f;
+    const int kmax = i < T - 1 ? i : T - 1;
+    for (int k = 0; k <= kmax; ++k) {
+        const long long s = (long long)b * S + (long long)(i - k) * N + p;
+        float xr, xi;
+        if (U8) {
+            const uchar2 q = reinterpret_cast<const uchar2 *>(in)[s];
+            xr = (float)q.x - mi;
+            xi = (float)q.y - mq;
+        } else {
+            const float2 q = reinterpret_cast<const float2 *>(in)[s];
+            xr = q.x;
+            xi = q.y;
+        }
+        const float h = taps[(long long)k * N + p];
+        ar = fmaf(h, xr, ar);
+        ai = fmaf(h, xi, ai);
+    }
+    w[((long long)b * P + i) * N + p] = make_float2(ar, ai);
+}
+
+// ---------------------------------------------------------------------------
+// Batched forward/inverse FFT of length N = 2^logN <= 4096, one row per CTA,
+// radix-2 Stockham autosort in shared memory.  phase_post: multiply bin c by
+// exp(-2*pi*i*c/N) (SURVEY App. A.4 factor, so rows equal channelize_poly's).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                       int N, int logN, int inverse, int phase_post) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufB = bufA + N;
+    const long long row = blockIdx.x;
+    const float2 *src = in + row * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) bufA[j] = src[j];
+    __syncthreads();
+    const int half = N >> 1;
+    const float sgn = inverse ? 1.f : -1.f;
+    for (int s = 0; s < logN; ++s) {
+        const int Ns = 1 << s;
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            const int k = j & (Ns - 1);
+            float sn, cs;
+            sincospif(sgn * (float)k / (float)Ns, &sn, &cs);
+            const float2 v0 = bufA[j];
+            const float2 a = bufA[j + half];
+            const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
+            const int j0 = ((j - k) << 1) + k;
+            bufB[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+            bufB[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        float2 *tmp = bufA; bufA = bufB; bufB = tmp;
+    }
+    float2 *dst = out + row * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float2 v = bufA[j];
+        if (phase_post) {
+            float sn, cs;
+            sincospif(-2.f * (float)j / (float)N, &sn, &cs);
+            v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+        }
+        dst[j] = v;
+    }
+}
+
+// One radix-2 Stockham pass over global memory (any length M = 2^m, batch rows
+// of length M).  Used for transforms that do not fit one CTA: the 2n-point
+// lag-search FFTs and N > 4096 channelizers.   grid = (M/2/256, batch)
+__global__ void __launch_bounds__(256) stockham_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                            long long M, long long Ns, int inverse) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long half = M >> 1;
+    if (j >= half) return;
+    const float2 *src = in + (long long)blockIdx.y * M;
+    float2 *dst = out + (long long)blockIdx.y * M;
+    const long long k = j & (Ns - 1);
+    float sn, cs;
+    // k/Ns in double so that very long transforms keep exact twiddle arguments
+    sincospif((float)((inverse ? 1.0 : -1.0) * (double)k / (double)Ns), &sn, &cs);
+    const float2 v0 = src[j];
+    const float2 a = src[j + half];
+    const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
+    const long long j0 = ((j - k) << 1) + k;
+    dst[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+    dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+}
+
+// ---------------------------------------------------------------------------
+// X-engine over stored spectra: part_x[b][c] = sum_i F0*conj(F1), part_a = (sum|F0|^2, sum|F1|^2)
+// grid = (ceil(N/256), n_blocks)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xengine_kernel(const float2 *__restrict__ F0, const float2 *__restrict__ F1,
+                                                      int N, int P, float2 *__restrict__ part_x,
+                                                      float2 *__restrict__ part_a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (c >= N) return;
+    float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < P; ++i) {
+        const float2 f0 = F0[((long long)b * P + i) * N + c];
+        const float2 f1 = F1[((long long)b * P + i) * N + c];
+        xr = fmaf(f0.x, f1.x, fmaf(f0.y, f1.y, xr));
+        xi = fmaf(f0.y, f1.x, fmaf(-f0.x, f1.y, xi));
+        a0 = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, a0));
+        a1 = fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, a1));
+    }
+    part_x[(long long)b * N + c] = make_float2(xr, xi);
+    part_a[(long long)b * N + c] = make_float2(a0, a1);
+}
+
+// ---------------------------------------------------------------------------
+// finalize: rows in the reference's output order (effex.py:519-521):
+//   out[b][j] = conj(rot[c]) * (1/P) * sum_seg part_x[b*splits+seg][c],  c = (j + N/2) mod N
+// grid = (ceil(N/256), n_blocks)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__restrict__ part_x,
+                                                            const float2 *__restrict__ part_a, int N, int splits,
+                                                            float inv_frames, const float2 *__restrict__ rot,
+                                                            float2 *__restrict__ xspec, float *__restrict__ auto0,
+                                                            float *__restrict__ auto1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= N) return;
+    const int c = (j + (N >> 1)) & (N - 1);
+    float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const long long o = ((long long)b * splits + s) * N + c;
+        const float2 x = part_x[o];
+        const float2 a = part_a[o];
+        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+    }
+    xr *= inv_frames; xi *= inv_frames;
+    const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);
+    // X * conj(rot)
+    xspec[(long long)b * N + j] = make_float2(xr * r.x + xi * r.y, xi * r.x - xr * r.y);
+    if (auto0) auto0[(long long)b * N + j] = a0 * inv_frames;
+    if (auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
+}
+
+// integrate: float64 accumulators += sum over all segments of the call (natural order, no rot)
+__global__ void __launch_bounds__(256) integrate_kernel(const float2 *__restrict__ part_x,
+                                                        const float2 *__restrict__ part_a, int N, int n_segs,
+                                                        double frames, double *__restrict__ acc_x,
+                                                        double *__restrict__ acc_a0, double *__restrict__ acc_a1,
+                                                        double *__restrict__ acc_frames) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double xr = 0, xi = 0, a0 = 0, a1 = 0;
+    for (int s = 0; s < n_segs; ++s) {
+        const float2 x = part_x[(long long)s * N + c];
+        const float2 a = part_a[(long long)s * N + c];
+        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+    }
+    acc_x[2 * c] += xr;
+    acc_x[2 * c + 1] += xi;
+    acc_a0[c] += a0;
+    acc_a1[c] += a1;
+    if (c == 0 && acc_frames) *acc_frames += frames;
+}
+
+// ---------------------------------------------------------------------------
+// Lag search (effex.py:583-622)
+// ---------------------------------------------------------------------------
+// zero-padded load of one block pair into two rows of length M (row 0 = ch0, row 1 = ch1)
+template <bool U8>
+__global__ void __launch_bounds__(256) lag_load_kernel(const void *__restrict__ in0, const void *__restrict__ in1,
+                                                       long long n, long long M, long long block,
+                                                       const unsigned long long *__restrict__ sums, int dc_remove,
+                                                       float2 *__restrict__ rows) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= M) return;
+    const int ch = blockIdx.y;
+    float2 v = make_float2(0.f, 0.f);
+    if (s < n) {
+        if (U8) {
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(ch ? in1 : in0) + 2ll * n * block;
+            float mi = 127.5f, mq = 127.5f;
+            if (dc_remove) {
+                mi = (float)((double)sums[4 * block + 2 * ch] / (double)n);
+                mq = (float)((double)sums[4 * block + 2 * ch + 1] / (double)n);
+            }
+            const uchar2 q = reinterpret_cast<const uchar2 *>(base)[s];
+            v = make_float2(((float)q.x - mi) * (1.0f / 127.5f), ((float)q.y - mq) * (1.0f / 127.5f));
+        } else {
+            const float2 *base = reinterpret_cast<const float2 *>(ch ? in1 : in0) + n * block;
+            v = base[s];
+        }
+    }
+    rows[(long long)ch * M + s] = v;
+}
+
+// acc[k] (+)= A[k]*conj(B[k])
+__global__ void __launch_bounds__(256) lag_accum_kernel(const float2 *__restrict__ rows, long long M, int first,
+                                                        float2 *__restrict__ acc) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const float2 a = rows[k], b = rows[M + k];
+    float2 r = make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    if (!first) { const float2 o = acc[k]; r.x += o.x; r.y += o.y; }
+    acc[k] = r;
+}
+
+struct ArgMax {
+    float val;
+    long long idx;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+    // larger value wins; on ties the smaller index (numpy argmax = first maximum)
+    if (b.val > a.val || (b.val == a.val && b.idx < a.idx)) return b;
+    return a;
+}
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgMax b;
+        b.val = __shfl_xor_sync(0xffffffffu, a.val, o);
+        b.idx = __shfl_xor_sync(0xffffffffu, a.idx, o);
+        a = better(a, b);
+    }
+    return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax a) {
+    __shared__ float sval[32];
+    __shared__ long long sidx[32];
+    a = warp_argmax(a);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sval[warp] = a.val; sidx[warp] = a.idx; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        ArgMax b;
+        b.val = lane < nw ? sval[lane] : -1.f;
+        b.idx = lane < nw ? sidx[lane] : (1ll << 62);
+        a = warp_argmax(b);
+    }
+    return a;   // valid in warp 0
+}
+// xc_shift[j] = xc[(j - n) mod M], j in [0, 2n): linear lag j - n.
+__global__ void __launch_bounds__(256) lag_argmax_stage1(const float2 *__restrict__ xc, long long n, long long M,
+                                                         float *__restrict__ pval, long long *__restrict__ pidx) {
+    ArgMax best{-1.f, 1ll << 62};
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < 2 * n;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long l = j - n;
+        const float2 v = xc[l >= 0 ? l : l + M];
+        best = better(best, ArgMax{v.x * v.x + v.y * v.y, j});
+    }
+    best = block_argmax(best);
+    if (threadIdx.x == 0) { pval[blockIdx.x] = best.val; pidx[blockIdx.x] = best.idx; }
+}
+// out: idx[0] = imax ; nb[0..2] = |xc_shift[imax-1]|, |..[imax]|, |..[imax+1]| * scale (-1 = out of range)
+__global__ void __launch_bounds__(256) lag_argmax_stage2(const float2 *__restrict__ xc, long long n, long long M,
+                                                         const float *__restrict__ pval,
+                                                         const long long *__restrict__ pidx, int nparts, float scale,
+                                                         long long *__restrict__ out_idx, float *__restrict__ out_nb) {
+    ArgMax best{-1.f, 1ll << 62};
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) best = better(best, ArgMax{pval[i], pidx[i]});
+    best = block_argmax(best);
+    if (threadIdx.x == 0) {
+        const long long imax = best.idx;
+        out_idx[0] = imax;
+        for (int d = -1; d <= 1; ++d) {
+            long long j = imax + d;
+            float r = -1.f;
+            if (j < 0) j += 2 * n;            // python negative index wraps (xcorr[-1])
+            if (j < 2 * n) {
+                const long long l = j - n;
+                const float2 v = xc[l >= 0 ? l : l + M];
+                r = sqrtf(v.x * v.x + v.y * v.y) * scale;
+            }
+            out_nb[d + 1] = r;
+        }
+    }
+}
+
+}  // namespace generic
+}  // namespace fx

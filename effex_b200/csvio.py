@@ -1,0 +1,56 @@
+"""effex `.csv` output (effex.py:667-693) and its reader conventions
+(effex.py:785-798, post_process.py:201-219).
+
+Line 1: `run_time:..,bandwidth:..,frequency:..,num_samp:..,resolution:..,gain:..,mode:..`
+Line 2 (SPECTRUM only): fftshifted bin frequencies, `%.18e`, comma separated.
+Then one line per RUN block: complex values as ` (%.18e%+.18ej)`, comma separated
+(what `np.savetxt(fh, [row], delimiter=',')` writes for complex128).  float32
+results are widened to float64 before formatting so the text round-trips.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+
+def write_metadata(path, run_time, bandwidth, frequency, num_samp, nbins, gain, mode):
+    with open(path, 'w') as fh:
+        fh.write(f'run_time:{run_time},bandwidth:{bandwidth},frequency:{frequency},'
+                 f'num_samp:{num_samp},resolution:{nbins},gain:{gain},mode:{mode}\n')
+        if mode == 'SPECTRUM':
+            freqs = np.fft.fftshift(np.fft.fftfreq(nbins, d=1 / bandwidth)) + frequency
+            np.savetxt(fh, [freqs], delimiter=',')
+        else:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                np.savetxt(fh, [])
+
+
+def format_rows(rows) -> str:
+    rows = np.asarray(rows)
+    if rows.ndim == 1:
+        rows = rows.reshape(1, -1)
+    rows = rows.astype(np.complex128)
+    out = []
+    for r in rows:
+        out.append(','.join((' (%.18e%+.18ej)' % (v.real, v.imag)) for v in r))
+    return '\n'.join(out) + '\n'
+
+
+def append_rows(path, rows):
+    with open(path, 'a') as fh:
+        fh.write(format_rows(rows))
+
+
+def read_metadata(path) -> dict:
+    with open(path) as fh:
+        first = fh.readline().strip()
+    return dict(item.split(':') for item in first.split(','))
+
+
+def read_rows(path):
+    """What effex.py:798 / post_process.py:219 do."""
+    meta = read_metadata(path)
+    skip = 1 if meta['mode'].lower() in ('continuum', 'test') else 2
+    return meta, np.loadtxt(path, dtype=np.complex128, delimiter=',', skiprows=skip, ndmin=2)

@@ -1,0 +1,239 @@
+"""FxEngine: thin Python face of the C ABI (one handle = one GPU, one shape).
+
+PyTorch is used here only for device memory and stream ordering; every kernel
+that runs is ours, launched by libeffex_fx.so through ctypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.signal
+import torch
+
+from . import _lib
+
+
+class FxError(RuntimeError):
+    pass
+
+
+def pfb_window(ntaps: int, nbins: int) -> np.ndarray:
+    """Prototype filter of effex.py:126-127 (float64, host)."""
+    L = int(ntaps) * int(nbins)
+    return (scipy.signal.get_window("hamming", L)
+            * scipy.signal.firwin(L, cutoff=1.0 / nbins, window="rectangular"))
+
+
+def rot_vector(nbins: int, bandwidth: float, frequency: float, delay: float) -> np.ndarray:
+    """rot[c] of effex.py:516-519 in float64, phase reduced mod 1 cycle before
+    exp so the float32 copy on the device keeps ~1e-7 accuracy."""
+    freqs = np.fft.fftfreq(nbins, d=1.0 / bandwidth) + frequency
+    cycles = np.mod(freqs * delay, 1.0)
+    return np.exp(2j * np.pi * cycles)
+
+
+def _raise(lib, handle, rc, what):
+    msg = lib.fx_last_error(handle)
+    msg = msg.decode() if msg else ""
+    text = f"{what} failed ({rc}): {msg}"
+    if rc in (_lib.FX_ERR_INVALID, _lib.FX_ERR_UNSUPPORTED):
+        raise ValueError(text)
+    raise FxError(text)
+
+
+class FxEngine:
+    def __init__(self, num_samp: int, nbins: int, ntaps: int = 4, device: int = 0, max_blocks: int = 1,
+                 dc_remove: bool = True, force_generic: bool = False, window: np.ndarray | None = None):
+        self.lib = _lib.load()
+        self.num_samp, self.nbins, self.ntaps = int(num_samp), int(nbins), int(ntaps)
+        self.device = int(device)
+        self.max_blocks = int(max_blocks)
+        cfg = _lib.FxConfig(self.device, self.ntaps, self.nbins, 1 if dc_remove else 0, self.num_samp,
+                            self.max_blocks, _lib.FX_FLAG_FORCE_GENERIC if force_generic else 0)
+        h = C.c_void_p()
+        rc = self.lib.fx_create(C.byref(cfg), C.byref(h))
+        if rc != _lib.FX_OK:
+            _raise(self.lib, None, rc, "fx_create")
+        self.h = h
+        self.frames_per_block = self.num_samp // self.nbins
+        self.tdev = torch.device("cuda", self.device)
+        self.stream = torch.cuda.ExternalStream(self.lib.fx_stream(self.h), device=self.tdev)
+        self.set_window(pfb_window(self.ntaps, self.nbins) if window is None else window)
+
+    # ---- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != _lib.FX_OK:
+            _raise(self.lib, self.h, rc, what)
+
+    @property
+    def fused(self) -> bool:
+        return bool(self.lib.fx_uses_fused(self.h))
+
+    def sync(self):
+        self._check(self.lib.fx_sync(self.h), "fx_sync")
+
+    # ---- parameters -------------------------------------------------------
+    def set_window(self, window):
+        w = np.ascontiguousarray(np.asarray(window, dtype=np.float64))
+        self._check(self.lib.fx_set_taps(self.h, w.ctypes.data_as(C.POINTER(C.c_double)), w.size), "fx_set_taps")
+        self.window = w
+
+    def set_rot(self, rot):
+        if rot is None:
+            self._check(self.lib.fx_set_rot(self.h, None, 0), "fx_set_rot")
+            return
+        r = np.ascontiguousarray(np.asarray(rot, dtype=np.complex128)).view(np.float64)
+        self._check(self.lib.fx_set_rot(self.h, r.ctypes.data_as(C.POINTER(C.c_double)), r.size // 2), "fx_set_rot")
+
+    def set_delay(self, bandwidth: float, frequency: float, delay: float):
+        self.set_rot(rot_vector(self.nbins, bandwidth, frequency, delay))
+
+    # ---- stream ordering with torch ----------------------------------------
+    def _enter(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.tdev))
+
+    def _exit(self):
+        torch.cuda.current_stream(self.tdev).wait_stream(self.stream)
+
+    def _raw(self, t: torch.Tensor, n_blocks: int) -> int:
+        if t.dtype != torch.uint8 or not t.is_cuda or t.device.index != self.device or not t.is_contiguous():
+            raise ValueError("raw IQ must be a contiguous uint8 CUDA tensor on the engine's device")
+        if t.numel() < 2 * self.num_samp * n_blocks:
+            raise ValueError("raw IQ tensor is shorter than n_blocks * 2 * num_samp bytes")
+        return t.data_ptr()
+
+    # ---- hot path -----------------------------------------------------------
+    def process(self, iq0: torch.Tensor, iq1: torch.Tensor, n_blocks: int | None = None, autos: bool = False,
+                out=None):
+        """fx_process: one fftshifted, rot-applied cross-spectrum row per block."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        if out is None:
+            x = torch.empty((n_blocks, self.nbins), dtype=torch.complex64, device=self.tdev)
+            a0 = torch.empty((n_blocks, self.nbins), dtype=torch.float32, device=self.tdev) if autos else None
+            a1 = torch.empty((n_blocks, self.nbins), dtype=torch.float32, device=self.tdev) if autos else None
+        else:
+            x, a0, a1 = out
+        self._enter()
+        rc = self.lib.fx_process(self.h, p0, p1, n_blocks, x.data_ptr(),
+                                 a0.data_ptr() if a0 is not None else None,
+                                 a1.data_ptr() if a1 is not None else None)
+        self._check(rc, "fx_process")
+        self._exit()
+        return (x, a0, a1) if autos else x
+
+    def new_accumulators(self):
+        z = lambda n: torch.zeros(n, dtype=torch.float64, device=self.tdev)
+        return {"x": z(2 * self.nbins), "a0": z(self.nbins), "a1": z(self.nbins), "frames": z(1)}
+
+    def integrate(self, iq0, iq1, acc, n_blocks: int | None = None):
+        """fx_integrate: add this call's un-normalised sums into float64 accumulators."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        self._enter()
+        rc = self.lib.fx_integrate(self.h, p0, p1, n_blocks, acc["x"].data_ptr(), acc["a0"].data_ptr(),
+                                   acc["a1"].data_ptr(), acc["frames"].data_ptr())
+        self._check(rc, "fx_integrate")
+        self._exit()
+        return acc
+
+    @staticmethod
+    def finish_integration(acc, rot=None):
+        """Host epilogue of an integration (after any cross-GPU reduce):
+        1/frames, conj(rot), fftshift -- effex.py:519-521 in float64."""
+        frames = float(acc["frames"].item())
+        x = acc["x"].cpu().numpy().view(np.complex128) / frames
+        if rot is not None:
+            x = x * np.conj(rot)
+        a0 = acc["a0"].cpu().numpy() / frames
+        a1 = acc["a1"].cpu().numpy() / frames
+        return np.fft.fftshift(x), np.fft.fftshift(a0), np.fft.fftshift(a1)
+
+    def process_host(self, raw0: np.ndarray, raw1: np.ndarray, n_blocks: int | None = None, autos: bool = False,
+                     out: np.ndarray | None = None):
+        """fx_process_host: HOST uint8 buffers in, HOST complex64 rows out (H2D/D2H inside)."""
+        if n_blocks is None:
+            n_blocks = raw0.size // (2 * self.num_samp)
+        for r in (raw0, raw1):
+            if r.dtype != np.uint8 or not r.flags.c_contiguous or r.size < 2 * self.num_samp * n_blocks:
+                raise ValueError("raw IQ must be contiguous uint8 of at least n_blocks*2*num_samp bytes")
+        x = np.empty((n_blocks, self.nbins), dtype=np.complex64) if out is None else out
+        a0 = np.empty((n_blocks, self.nbins), dtype=np.float32) if autos else None
+        a1 = np.empty((n_blocks, self.nbins), dtype=np.float32) if autos else None
+        rc = self.lib.fx_process_host(self.h, raw0.ctypes.data, raw1.ctypes.data, n_blocks, x.ctypes.data,
+                                      a0.ctypes.data if autos else None, a1.ctypes.data if autos else None)
+        self._check(rc, "fx_process_host")
+        return (x, a0, a1) if autos else x
+
+    # ---- pieces ---------------------------------------------------------------
+    def pfb(self, x) -> torch.Tensor:
+        """_spectrometer_poly: complex input of num_samp samples -> (P, N) complex64."""
+        if isinstance(x, torch.Tensor) and x.dtype == torch.uint8:
+            p = self._raw(x, 1)
+            out = torch.empty((self.frames_per_block, self.nbins), dtype=torch.complex64, device=self.tdev)
+            self._enter()
+            self._check(self.lib.fx_pfb_u8(self.h, p, out.data_ptr()), "fx_pfb_u8")
+            self._exit()
+            return out
+        xt = self._as_c64(x)
+        if xt.numel() != self.num_samp:
+            raise ValueError("input length must equal the engine's num_samp")
+        out = torch.empty((self.frames_per_block, self.nbins), dtype=torch.complex64, device=self.tdev)
+        self._enter()
+        self._check(self.lib.fx_pfb_c64(self.h, xt.data_ptr(), out.data_ptr()), "fx_pfb_c64")
+        self._exit()
+        return out
+
+    def _as_c64(self, x) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.tdev, dtype=torch.complex64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x).astype(np.complex64))).to(self.tdev)
+
+    def lag(self, a, b, n_blocks: int = 1):
+        """Lag search of effex.py:605-622.  Returns (n, imax, xprev, xbest, xnext)."""
+        imax = C.c_int64()
+        nb = (C.c_float * 3)()
+        if isinstance(a, torch.Tensor) and a.dtype == torch.uint8:
+            p0, p1 = self._raw(a, n_blocks), self._raw(b, n_blocks)
+            self._enter()
+            rc = self.lib.fx_lag_u8(self.h, p0, p1, n_blocks, C.byref(imax), nb)
+        else:
+            if len(a) != len(b):
+                raise AssertionError('Algorithm assumes input complex timeseries are of equal length.')
+            ta, tb = self._as_c64(a), self._as_c64(b)
+            if ta.numel() != self.num_samp * n_blocks:
+                raise ValueError("input length must equal n_blocks * num_samp")
+            self._enter()
+            rc = self.lib.fx_lag_c64(self.h, ta.data_ptr(), tb.data_ptr(), n_blocks, C.byref(imax), nb)
+        self._check(rc, "fx_lag")
+        return self.num_samp, int(imax.value), float(nb[0]), float(nb[1]), float(nb[2])
+
+    # ---- measurement -----------------------------------------------------------
+    def reset_counters(self):
+        self._check(self.lib.fx_reset_counters(self.h), "fx_reset_counters")
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.fx_kernel_launches(self.h))
+
+    def enable_timing(self, on: bool = True):
+        self._check(self.lib.fx_enable_timing(self.h, 1 if on else 0), "fx_enable_timing")
+
+    def dominant_kernel_time(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        self._check(self.lib.fx_dominant_kernel_time(self.h, C.byref(ms), C.byref(n)), "fx_dominant_kernel_time")
+        return float(ms.value), int(n.value)

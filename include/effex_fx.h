@@ -1,0 +1,158 @@
+/* effex_fx.h -- C ABI of the B200-native FX-correlator hot path (libeffex_fx.so).
+ *
+ * Drop-in boundary for the DSP region of evanmayer/effex.  The reference has
+ * no FFI layer of its own: its hot path is five private methods of
+ * `Correlator` that call cupy/cuSignal (effex/effex.py:476-627).  Each entry
+ * point below names the reference lines it replaces; `INTEGRATION.md` shows
+ * the ctypes stub a maintainer would add to effex.py.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no C++/torch types.
+ *   - every call returns 0 (FX_OK) or a negative fx_status; the message for
+ *     the last failure on a handle is fx_last_error(h) (NULL handle: the last
+ *     failure of fx_create on this thread).
+ *   - pointers named d_* are DEVICE pointers on the handle's device and stay
+ *     owned by the caller; h_* are HOST pointers.  The handle owns taps,
+ *     twiddles, workspaces and its stream.
+ *   - calls are asynchronous on the handle's stream unless stated; fx_sync()
+ *     waits.  A handle is not re-entrant (the reference calls this path from
+ *     one thread, effex/effex.py:399-410).
+ *   - there is NO CPU fallback: without a CUDA device fx_create fails.
+ *
+ * Data layout
+ *   raw IQ    uint8, interleaved I,Q, one array per channel (RTL-SDR format,
+ *             what pyrtlsdr's packed_bytes_to_iq consumes: x=(b/127.5-1)).
+ *             A "block" is num_samp complex samples (2*num_samp bytes); blocks
+ *             of one call are contiguous.
+ *   spectra   complex64 as float pairs (re,im).  Cross-spectra rows are in
+ *             the order effex writes them (fftshifted, effex.py:521).
+ */
+#ifndef EFFEX_FX_H
+#define EFFEX_FX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_ABI_VERSION 1
+
+typedef enum {
+    FX_OK = 0,
+    FX_ERR_INVALID = -1,      /* bad argument (Python wrapper raises ValueError)      */
+    FX_ERR_CUDA = -2,         /* CUDA runtime failure                                  */
+    FX_ERR_UNSUPPORTED = -3,  /* shape outside the supported set (e.g. ntaps > 32)     */
+    FX_ERR_STATE = -4         /* call order (e.g. fx_process before fx_set_taps)       */
+} fx_status;
+
+typedef struct fx_handle fx_handle;
+
+typedef struct {
+    int32_t device;       /* CUDA device ordinal                                           */
+    int32_t ntaps;        /* T, PFB taps per branch (effex.py:115 uses 4; cuSignal cap 32) */
+    int32_t nbins;        /* N = --resolution, power of two, 8..65536                      */
+    int32_t dc_remove;    /* 1: per-block DC removal of effex.py:394-395; 0: none          */
+    int64_t num_samp;     /* S complex samples per block (effex.py:87, --num_samp)         */
+    int32_t max_blocks;   /* capacity: blocks per fx_process / fx_integrate call           */
+    int32_t flags;        /* FX_FLAG_* bit mask                                            */
+} fx_config;
+
+#define FX_FLAG_FORCE_GENERIC 1   /* never take the fused kernels (used to cross-check them) */
+
+/* ---- lifetime --------------------------------------------------------- */
+int fx_abi_version(void);
+int fx_device_count(void);
+/* Replaces Correlator.__init__'s GPU set-up (effex.py:109-127). */
+int fx_create(const fx_config *cfg, fx_handle **out);
+int fx_destroy(fx_handle *h);
+const char *fx_last_error(const fx_handle *h);
+int fx_sync(fx_handle *h);
+/* 1 if fx_process on this handle runs the fused unpack->PFB->FFT->X kernel. */
+int fx_uses_fused(const fx_handle *h);
+
+/* ---- parameters --------------------------------------------------------
+ * fx_set_taps: prototype filter h[T*N] in the reference's order, float64, as
+ * built on the host by `get_window("hamming",T*N)*firwin(T*N,1/N,'rectangular')`
+ * (effex.py:126-127).  Synchronous.                                         */
+int fx_set_taps(fx_handle *h, const double *h_taps, size_t n);
+/* fx_set_rot: rot[c], c in natural FFT order, as (re,im) float64 pairs,
+ * = exp(+2j*pi*(fftfreq(N,1/bw)[c]+fc)*tau) (effex.py:516-519); built in
+ * float64 on the host because the phase spans ~1e4 cycles.  NULL = all ones. */
+int fx_set_rot(fx_handle *h, const double *h_rot_re_im, size_t nbins);
+
+/* ---- the hot path ------------------------------------------------------
+ * fx_process: for each of n_blocks block pairs, what one RUN trip of the loop
+ * does (effex.py:391-395 DC removal, :490-527 _run_task/_pfb_xcorr):
+ *   d_xspec[b][j]  (complex64, [n_blocks][N])  = fftshift(mean_i F0*conj(F1*rot))
+ *   d_auto0/1[b][j] (float32, [n_blocks][N], may be NULL) = fftshift(mean_i |Fk|^2)
+ * Input: d_iq0/d_iq1 uint8[n_blocks][2*num_samp].                           */
+int fx_process(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+               float *d_xspec, float *d_auto0, float *d_auto1);
+
+/* fx_integrate: same per-block arithmetic, but ADDS the un-normalised sums
+ * over all frames of all n_blocks blocks into float64 accumulators in
+ * natural bin order, without rot:
+ *   d_acc_x[c] (re,im) += sum F0*conj(F1); d_acc_a0[c] += sum|F0|^2; d_acc_a1 likewise
+ *   *d_frames += number of frames added.
+ * These are the small per-integration accumulators that are reduced across
+ * GPUs (one NCCL reduce) before the host applies 1/frames, rot and fftshift. */
+int fx_integrate(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                 double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
+
+/* fx_process_host: fx_process with HOST buffers (pinned or pageable): H2D of
+ * the raw bytes, compute, D2H of the rows, pipelined in chunks on two
+ * streams.  Synchronous.  This is the call the reference-facing wrapper
+ * makes per batch of dequeued blocks (effex.py:391-410 + :693 asnumpy).     */
+int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks,
+                    float *h_xspec, float *h_auto0, float *h_auto1);
+
+/* ---- pieces exposed for the reference's own tests -----------------------
+ * fx_pfb_c64: Correlator._spectrometer_poly(x, ntaps, n_branches, window)
+ * (effex.py:530-555) on a complex64 device array of num_samp samples:
+ * d_frames[i][c], [P][N] complex64, P = num_samp / N, INCLUDING the
+ * exp(-2j*pi*c/N) factor so it equals cuSignal's channelize_poly(...).T.     */
+int fx_pfb_c64(fx_handle *h, const float *d_x, float *d_frames);
+/* fx_pfb_u8: same from raw bytes of one block (unpack + DC removal first).  */
+int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames);
+
+/* ---- delay calibration --------------------------------------------------
+ * Correlator._estimate_delay_gaussian (effex.py:583-622): zero-pad to 2n,
+ * xc = fftshift(ifft(fft(a)*conj(fft(b)))), imax = argmax|xc| (first max),
+ * and the three magnitudes |xc[imax-1]|,|xc[imax]|,|xc[imax+1]|.  The host
+ * does the float64 log-parabola (:623-627).  n = num_samp of the handle.
+ * With n_blocks > 1 the 2n-point cross-spectrum is accumulated over the
+ * blocks before the single inverse FFT (BASELINE config 2).  Synchronous.
+ * Integer lag = n - imax.  nbhd[k] = -1 marks an out-of-range neighbour
+ * (the reference raises IndexError there, effex.py:619 TODO).                */
+int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blocks,
+               int64_t *imax, float nbhd[3]);
+int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+              int64_t *imax, float nbhd[3]);
+
+/* ---- memory helpers (so a non-torch host can drive the library) --------- */
+int fx_dev_alloc(fx_handle *h, size_t bytes, void **d_ptr);
+int fx_dev_free(fx_handle *h, void *d_ptr);
+int fx_host_alloc_pinned(size_t bytes, void **h_ptr);
+int fx_host_free_pinned(void *h_ptr);
+int fx_memcpy_h2d(fx_handle *h, void *d_dst, const void *h_src, size_t bytes);
+int fx_memcpy_d2h(fx_handle *h, void *h_dst, const void *d_src, size_t bytes);
+int fx_memset(fx_handle *h, void *d_ptr, int value, size_t bytes);
+
+/* ---- measurement --------------------------------------------------------
+ * Counters since the last fx_reset_counters: kernels this library launched,
+ * and device time of the dominant (fused / FFT) kernel measured with CUDA
+ * events on the handle's stream when timing is enabled.                     */
+int fx_reset_counters(fx_handle *h);
+int64_t fx_kernel_launches(const fx_handle *h);
+int fx_enable_timing(fx_handle *h, int on);
+/* ms spent in, and launches of, the dominant kernel while timing was on. */
+int fx_dominant_kernel_time(fx_handle *h, double *ms_total, int64_t *launches);
+/* raw cudaStream_t of the handle (so a torch host can wait/record on it). */
+void *fx_stream(fx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFEX_FX_H */

@@ -1,0 +1,229 @@
+"""GPU parity: the CUDA path (through the C ABI) against the float64 oracle.
+
+Bars (BASELINE.json north_star): accumulated cross-spectra within 1e-4
+relative (max-norm and L2-norm) of the float64 oracle; the
+integer delay lag bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fx_oracle as orc
+from effex_b200 import synth
+from effex_b200.engine import FxEngine, rot_vector
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4      # north_star tolerance, float32 GPU vs float64 reference
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.complex128)
+    ref = np.asarray(ref, dtype=np.complex128)
+    return (np.abs(got - ref).max() / np.abs(ref).max(),
+            np.linalg.norm(got - ref) / np.linalg.norm(ref))
+
+
+def assert_close(got, ref, tol=TOL, what=""):
+    e_max, e_l2 = rel_err(got, ref)
+    assert e_max <= tol and e_l2 <= tol, f"{what}: max-norm {e_max:.3e}, L2 {e_l2:.3e} > {tol}"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def oracle_rows(raw0, raw1, S, N, bw, fc, tau, nblocks, ntaps=4):
+    return orc.process_recording_u8(raw0, raw1, S, N, bw, fc, tau, ntaps, 0, nblocks)
+
+
+def oracle_autos(raw0, raw1, S, N, b, ntaps=4):
+    sl = slice(2 * S * b, 2 * S * (b + 1))
+    return orc.auto_powers(orc.block_from_u8(raw0[sl]), orc.block_from_u8(raw1[sl]), ntaps, N,
+                           orc.pfb_window(ntaps, N))
+
+
+# --------------------------------------------------------------------------
+# canonical config C1: S = 2^18, N = 4096, T = 4 -> fused kernel
+# --------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c1():
+    S, N, nb = 2**18, 4096, 6
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=37, dc0=0.011 - 0.007j, dc1=-0.004 + 0.015j)
+    return dict(S=S, N=N, nb=nb, raw0=raw0, raw1=raw1, bw=2.4e6, fc=1.4204e9)
+
+
+@pytest.mark.parametrize("tau_samples", [0.0, 37.0])
+def test_fused_canonical_vs_oracle(c1, tau_samples):
+    S, N, nb = c1["S"], c1["N"], c1["nb"]
+    tau = tau_samples / c1["bw"]
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    assert eng.fused
+    eng.set_delay(c1["bw"], c1["fc"], tau)
+    x, a0, a1 = eng.process(dev(c1["raw0"]), dev(c1["raw1"]), nb, autos=True)
+    eng.sync()
+    ref = oracle_rows(c1["raw0"], c1["raw1"], S, N, c1["bw"], c1["fc"], tau, nb)
+    got = x.cpu().numpy()
+    for b in range(nb):
+        assert_close(got[b], ref[b], what=f"block {b}")
+    r0, r1 = oracle_autos(c1["raw0"], c1["raw1"], S, N, 1)
+    assert_close(a0[1].cpu().numpy(), r0, what="auto0")
+    assert_close(a1[1].cpu().numpy(), r1, what="auto1")
+    eng.close()
+
+
+def test_fused_equals_generic_path(c1):
+    S, N, nb = c1["S"], c1["N"], 3
+    d0, d1 = dev(c1["raw0"]), dev(c1["raw1"])
+    ef = FxEngine(S, N, 4, max_blocks=nb)
+    eg = FxEngine(S, N, 4, max_blocks=nb, force_generic=True)
+    assert ef.fused and not eg.fused
+    xf = ef.process(d0, d1, nb).cpu().numpy()
+    xg = eg.process(d0, d1, nb).cpu().numpy()
+    for b in range(nb):
+        assert_close(xf[b], xg[b], tol=2e-5, what=f"fused vs generic block {b}")
+    ef.close(); eg.close()
+
+
+@pytest.mark.parametrize("nb", [1, 2, 5, 149, 300])
+def test_fused_segment_plans_agree(c1, nb):
+    """Every block count picks its own split of blocks into segments; rows must not
+    depend on it.  Input = 2 distinct blocks tiled."""
+    S, N = c1["S"], c1["N"]
+    base0, base1 = c1["raw0"][:4 * S], c1["raw1"][:4 * S]
+    raw0 = np.tile(base0, (nb + 1) // 2)[:2 * S * nb]
+    raw1 = np.tile(base1, (nb + 1) // 2)[:2 * S * nb]
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    ref = oracle_rows(base0, base1, S, N, 2.4e6, 1.4204e9, 0.0, min(nb, 2))
+    for b in range(nb):
+        assert_close(x[b], ref[b % 2], what=f"nb={nb} block {b}")
+        if b >= 2:      # identical input blocks -> bit-identical rows, whatever CTA took them
+            np.testing.assert_array_equal(x[b], x[b - 2])
+    eng.close()
+
+
+def test_fused_large_dc_offset():
+    S, N = 2**16, 4096
+    raw0, raw1 = synth.correlated_pair(S, delay=3, dc0=0.09 + 0.05j, dc1=-0.07 - 0.11j, seed=5)
+    eng = FxEngine(S, N, 4)
+    assert eng.fused
+    x = eng.process(dev(raw0), dev(raw1), 1).cpu().numpy()[0]
+    ref = orc.process_block_u8(raw0, raw1, N, 2.4e6, 1.4204e9, 0.0)
+    assert_close(x, ref, what="large DC")
+    # without DC removal the spike at the centre bin would dominate
+    eng2 = FxEngine(S, N, 4, dc_remove=False)
+    y = eng2.process(dev(raw0), dev(raw1), 1).cpu().numpy()[0]
+    assert np.abs(y[N // 2]) > 20 * np.abs(x).max()
+    eng.close(); eng2.close()
+
+
+def test_integrate_matches_rows(c1):
+    S, N, nb = c1["S"], c1["N"], c1["nb"]
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    d0, d1 = dev(c1["raw0"]), dev(c1["raw1"])
+    rows = eng.process(d0, d1, nb).cpu().numpy().astype(np.complex128)
+    acc = eng.new_accumulators()
+    eng.integrate(d0[:2 * S * 4], d1[:2 * S * 4], acc, 4)
+    eng.integrate(d0[2 * S * 4:], d1[2 * S * 4:], acc, nb - 4)     # accumulates across calls
+    eng.sync()
+    assert acc["frames"].item() == nb * (S // N)
+    x, a0, a1 = FxEngine.finish_integration(acc)
+    assert_close(x, rows.mean(axis=0), tol=1e-6, what="integrate vs mean of rows")
+    ref = oracle_rows(c1["raw0"], c1["raw1"], S, N, c1["bw"], c1["fc"], 0.0, nb).mean(axis=0)
+    assert_close(x, ref, what="integrate vs oracle")
+    eng.close()
+
+
+def test_process_host_pipeline(c1):
+    S, N, nb = c1["S"], c1["N"], c1["nb"]
+    eng = FxEngine(S, N, 4, max_blocks=4)          # forces several chunks (6 blocks, <= 4 per chunk)
+    x = eng.process_host(c1["raw0"], c1["raw1"], nb)
+    ref = eng.process(dev(c1["raw0"])[:2 * S * 4], dev(c1["raw1"])[:2 * S * 4], 4).cpu().numpy()
+    np.testing.assert_array_equal(x[:4], ref)
+    full = oracle_rows(c1["raw0"], c1["raw1"], S, N, c1["bw"], c1["fc"], 0.0, nb)
+    for b in range(nb):
+        assert_close(x[b], full[b], what=f"host pipeline block {b}")
+    eng.close()
+
+
+# --------------------------------------------------------------------------
+# other shapes (generic kernels): C5-like N=1024, ragged S, small N, T up to 32
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("S,N,T", [(319488, 1024, 4), (4099, 2048, 2), (2**14, 256, 4), (2**15, 2048, 4),
+                                   (2**16, 512, 8), (3000, 64, 32), (2**17, 8192, 4)])
+def test_generic_shapes_vs_oracle(S, N, T):
+    nb = 2
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=2, dc0=0.02j, dc1=-0.01, seed=11)
+    w = orc.pfb_window(T, N)
+    eng = FxEngine(S, N, T, max_blocks=nb, window=w)
+    tau = 2 / 3.2e6
+    eng.set_delay(3.2e6, 1.0e8, tau)
+    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    ref = orc.process_recording_u8(raw0, raw1, S, N, 3.2e6, 1.0e8, tau, T, 0, nb)
+    for b in range(nb):
+        assert_close(x[b], ref[b], what=f"S={S} N={N} T={T} block {b}")
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden_reference_fixture(golden_dir, tag):
+    """Fixtures made by running the reference's own effex.py (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, f"ref_case_{tag}.npz"))
+    S, N, bw, fc = int(g["S"]), int(g["N"]), float(g["bw"]), float(g["fc"])
+    eng = FxEngine(S, N, 4)
+    d0, d1 = dev(g["raw0"]), dev(g["raw1"])
+    assert_close(eng.process(d0, d1, 1).cpu().numpy()[0], g["xspec_tau0"], what="xspec tau=0")
+    eng.set_delay(bw, fc, float(g["calibrated_delay"]))
+    assert_close(eng.process(d0, d1, 1).cpu().numpy()[0], g["xspec_cal"], what="xspec calibrated")
+    assert_close(eng.pfb(d0).cpu().numpy(), g["spec0"], what="spectrometer (u8)")
+    x0 = orc.block_from_u8(g["raw0"])
+    assert_close(eng.pfb(x0).cpu().numpy(), g["spec0"], what="spectrometer (c64)")
+    eng.close()
+
+
+# --------------------------------------------------------------------------
+# delay calibration: integer lag exact
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("nblk", [1, 4])
+def test_lag_u8_exact_c2(nblk):
+    S = 2**18
+    raw0, raw1 = synth.correlated_pair(nblk * S, delay=37, seed=123)
+    eng = FxEngine(S, 4096, 4, max_blocks=nblk)
+    n, imax, p, q, r = eng.lag(dev(raw0), dev(raw1), nblk)
+    blocks0 = [orc.block_from_u8(raw0[2 * S * b:2 * S * (b + 1)]) for b in range(nblk)]
+    blocks1 = [orc.block_from_u8(raw1[2 * S * b:2 * S * (b + 1)]) for b in range(nblk)]
+    rn, rimax, rp, rq, rr = orc.accumulated_lag_search(blocks0, blocks1)
+    assert n - imax == 37 and imax == rimax            # bit-exact integer lag
+    np.testing.assert_allclose([p, q, r], [rp, rq, rr], rtol=2e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [3 + 2**12, 2**18, 1000])
+@pytest.mark.parametrize("offset", [-2000, -1001, -1, 0, 1, 999, 2000])
+def test_lag_c64_exact(n, offset):
+    if abs(offset) >= n:
+        pytest.skip("offset outside the block")
+    iq0, iq1 = synth.rolled_pair(n, offset)
+    eng = FxEngine(n, 8, 1)
+    gn, imax, p, q, r = eng.lag(iq0, iq1)
+    rn, rimax, rp, rq, rr = orc.lag_search(iq0, iq1)
+    assert imax == rimax and gn - imax == offset
+    np.testing.assert_allclose([p, q, r], [rp, rq, rr], rtol=1e-3, atol=1e-7 * rq)
+    eng.close()
+
+
+def test_errors_are_value_errors():
+    with pytest.raises(ValueError):
+        FxEngine(2**18, 4096, 33)
+    with pytest.raises(ValueError):
+        FxEngine(2**18, 3000, 4)
+    eng = FxEngine(2**14, 1024, 4, max_blocks=1)
+    raw = torch.zeros(4 * 2**14, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        eng.process(raw, raw, 2)               # exceeds max_blocks
+    with pytest.raises(ValueError):
+        eng.process(raw.cpu(), raw.cpu(), 1)   # host tensor on the device entry point
+    eng.close()
