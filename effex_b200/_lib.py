@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeffex_fx.so")
+LIB_PATH = os.environ.get("EFFEX_FX_LIB") or os.path.join(HERE, "libeffex_fx.so")   # env: experiment variants only
 
 FX_OK = 0
 FX_ERR_INVALID = -1
@@ -39,6 +39,7 @@ SIGNATURES = {
     "fx_set_rot": (C.c_int, [_VP, C.POINTER(C.c_double), C.c_size_t]),
     "fx_process": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "fx_integrate": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "fx_process_acc": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "fx_process_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "fx_pfb_c64": (C.c_int, [_VP, _VP, _VP]),
     "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),

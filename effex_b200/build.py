@@ -33,11 +33,13 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines`/`out` build an experiment variant (tools/kbench.py); the product is the default."""
+    if out is None and not force and not _stale():
         return LIB
+    out = out or LIB
     cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -45,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libeffex_fx.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

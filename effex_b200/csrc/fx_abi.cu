@@ -344,10 +344,18 @@ int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long lon
 }
 
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
-                   float *d_auto0, float *d_auto1) {
+                   float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
+                   double *d_acc_a1 = nullptr, double *d_frames = nullptr) {
     int rc = run_parts(h, d_iq0, d_iq1, n_blocks);
     if (rc) return rc;
     const int N = h->cfg.nbins;
+    if (d_acc_x) {
+        const int n_segs = (int)(n_blocks * h->planned_splits);
+        fx::generic::integrate_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(
+            h->d_part_x, h->d_part_a, N, n_segs, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+        FX_LAUNCH_CHECK(h, "integrate");
+    }
+    if (!d_xspec) return FX_OK;
     dim3 grid((N + 255) / 256, 1);
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
         const long long nb = std::min<long long>(65535, n_blocks - b0);
@@ -429,7 +437,7 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     const int nparts = (int)std::min<long long>(1024, (2 * n + 255) / 256);
     fx::generic::lag_argmax_stage1<<<nparts, 256, 0, h->stream>>>(h->d_lag_acc, n, M, h->d_pval, h->d_pidx);
     FX_LAUNCH_CHECK(h, "lag_argmax_stage1");
-    const float scale = (float)(1.0 / ((double)M * 2.0 * (double)n));
+    const float scale = (float)(1.0 / (double)M);   // unnormalised inverse of length M -> ifft value
     fx::generic::lag_argmax_stage2<<<1, 256, 0, h->stream>>>(h->d_lag_acc, n, M, h->d_pval, h->d_pidx, nparts, scale,
                                                             h->d_lag_idx, h->d_lag_nb);
     FX_LAUNCH_CHECK(h, "lag_argmax_stage2");
@@ -611,18 +619,17 @@ int fx_process(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t
 
 int fx_integrate(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, double *d_acc_x,
                  double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+    return fx_process_acc(h, d_iq0, d_iq1, n_blocks, nullptr, nullptr, nullptr, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+}
+
+int fx_process_acc(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, float *d_xspec,
+                   float *d_auto0, float *d_auto1, double *d_acc_x, double *d_acc_a0, double *d_acc_a1,
+                   double *d_frames) {
     int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
     if (rc) return rc;
     if (!d_acc_x || !d_acc_a0 || !d_acc_a1) return fail(h, FX_ERR_INVALID, "null accumulator pointer");
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
-    rc = run_parts(h, d_iq0, d_iq1, n_blocks);
-    if (rc) return rc;
-    const int N = h->cfg.nbins;
-    const int n_segs = (int)(n_blocks * h->planned_splits);
-    fx::generic::integrate_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(
-        h->d_part_x, h->d_part_a, N, n_segs, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-    FX_LAUNCH_CHECK(h, "integrate");
-    return FX_OK;
+    return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
 }
 
 int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,

@@ -33,7 +33,8 @@ constexpr int RING = 3;          // raw-frame ring slots
 constexpr int FRAME_BYTES = 2 * N;   // per channel
 
 struct __align__(16) Smem {
-    float4 X[N];                 // 64 KB exchange buffer (re0,re1,im0,im1)
+    float2 Xr[N];                // 32 KB exchange plane: (re ch0, re ch1)
+    float2 Xi[N];                // 32 KB exchange plane: (im ch0, im ch1)   (must follow Xr: the epilogue uses both as one 64 KB buffer)
     float4 taps[N];              // 64 KB: taps[p] = h[kN+N-1-p]/127.5, k=0..3
     float2 twA[16][NT];          // W4096^(t*k1), row 0 unused
     float2 twB[16][16];          // W256^(n3*k2)
@@ -95,12 +96,38 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
-// byte j of a packed (I0,Q0,I1,Q1) word -> float(2^15 + byte), exact
+// Unpack of byte J of a packed (I0,Q0,I1,Q1) word.  Two exact routes to float(b - 128):
+//  * magic: PRMT the byte into the mantissa of 2^15 (ALU pipe), then one FADD2 per pair of
+//    components subtracts 2^15 + 128 (FMA pipe);
+//  * I2F.S8 Rd, Rs.BJ on the byte biased by 0x80: one instruction, but it issues on the XU
+//    pipe at 16 lanes/clk/SM (measured, profiles/), far too slow to use for all 16 conversions
+//    a point needs per frame.  kI2FTaps of the four taps use it to take work off the FMA pipe.
 template <int J>
 __device__ __forceinline__ float byte_to_magic(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (J << 4)));
 }
+template <int J>
+__device__ __forceinline__ float sbyte_to_float(uint32_t w) {
+    return (float)(int8_t)(((w ^ 0x80808080u) >> (8 * J)) & 0xffu);
+}
 constexpr float kMagic = 32768.0f + 128.0f;   // 2^15 + 128: f - kMagic = byte - 128, exact
+
+// (I, Q) channel pairs of one packed word as exact floats (b - 128)
+template <bool USE_I2F>
+__device__ __forceinline__ void unpack_pairs(uint32_t w, float2 &pi, float2 &pq) {
+    if (USE_I2F) {
+        pi = f2(sbyte_to_float<0>(w), sbyte_to_float<2>(w));
+        pq = f2(sbyte_to_float<1>(w), sbyte_to_float<3>(w));
+    } else {
+        const float2 mg = f2(-kMagic, -kMagic);
+        pi = f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg);
+        pq = f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg);
+    }
+}
+#ifndef FX_I2F_TAPS
+#define FX_I2F_TAPS 0
+#endif
+constexpr int kI2FTaps = FX_I2F_TAPS;    // how many of the 4 taps unpack through I2F.S8 (XU pipe)
 
 __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -121,6 +148,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
     const int lo = t & 15;     // n3 (stage B) / k2 (stage C)
     uint32_t ring_cnt = 0;     // ingest counter: slot = cnt % RING, parity = (cnt / RING) & 1
 
+    int already = 0;           // ingest items of the coming segment already issued by the previous one (thread 0)
     for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
         const Segment sg = prm.segs[seg];
         const uint8_t *b0 = prm.iq0 + 2ll * prm.S * sg.block;
@@ -141,14 +169,24 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
         // ingest frames g0 .. f0+nf-1 ; frames before f0 only fill the FIR history
         const int g0 = sg.f0 - (T - 1) > 0 ? sg.f0 - (T - 1) : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
+        // the segment after this one (same CTA): its first frames are prefetched during our last ones
+        const int nseg = seg + gridDim.x;
+        const bool have_next = nseg < prm.n_segs && n_ing >= RING;
+        Segment ng = sg;
+        if (have_next) ng = prm.segs[nseg];
+        const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
+        const int n_ing_next = have_next ? ng.f0 + ng.nf - ng0 : 0;
+        const uint8_t *nb0 = prm.iq0 + 2ll * prm.S * ng.block;
+        const uint8_t *nb1 = prm.iq1 + 2ll * prm.S * ng.block;
         if (t == 0) {
             const int pre = n_ing < RING ? n_ing : RING;
-            for (int j = 0; j < pre; ++j) {
+            for (int j = already; j < pre; ++j) {
                 const uint32_t s = (ring_cnt + j) % RING;
                 mbar_expect_tx(&sm.mbar[s], 2 * FRAME_BYTES);
                 tma_load_1d(&sm.raw[s][0][0], b0 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
                 tma_load_1d(&sm.raw[s][1][0], b1 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
             }
+            already = 0;
         }
 
         uint32_t hist[T - 1][16];     // packed (I0,Q0,I1,Q1) of frames i-1, i-2, i-3
@@ -171,7 +209,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             for (int r = 0; r < 16; ++r) {
                 const uint32_t a = sm.raw[slot][0][t + NT * r];
                 const uint32_t b = sm.raw[slot][1][t + NT * r];
-                cur[r] = __byte_perm(a, b, 0x5410);
+                cur[r] = __byte_perm(a, b, 0x5410);                 // (I0,Q0,I1,Q1)
             }
 
             const bool compute = fi >= sg.f0;
@@ -190,27 +228,19 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
                     const float hs = (tp.x + tp.y) + (tp.z + tp.w);
                     float2 ar = f2muls(nmI, hs);
                     float2 ai = f2muls(nmQ, hs);
-                    const float2 mg = f2(-kMagic, -kMagic);
-                    {
-                        const uint32_t w = cur[r];
-                        ar = f2fmas(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), tp.x, ar);
-                        ai = f2fmas(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), tp.x, ai);
-                    }
-                    {
-                        const uint32_t w = hist[0][r];
-                        ar = f2fmas(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), tp.y, ar);
-                        ai = f2fmas(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), tp.y, ai);
-                    }
-                    {
-                        const uint32_t w = hist[1][r];
-                        ar = f2fmas(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), tp.z, ar);
-                        ai = f2fmas(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), tp.z, ai);
-                    }
-                    {
-                        const uint32_t w = hist[2][r];
-                        ar = f2fmas(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), tp.w, ar);
-                        ai = f2fmas(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), tp.w, ai);
-                    }
+                    float2 pi, pq;
+                    unpack_pairs<(kI2FTaps > 0)>(cur[r], pi, pq);
+                    ar = f2fmas(pi, tp.x, ar);
+                    ai = f2fmas(pq, tp.x, ai);
+                    unpack_pairs<(kI2FTaps > 1)>(hist[0][r], pi, pq);
+                    ar = f2fmas(pi, tp.y, ar);
+                    ai = f2fmas(pq, tp.y, ai);
+                    unpack_pairs<(kI2FTaps > 2)>(hist[1][r], pi, pq);
+                    ar = f2fmas(pi, tp.z, ar);
+                    ai = f2fmas(pq, tp.z, ai);
+                    unpack_pairs<(kI2FTaps > 3)>(hist[2][r], pi, pq);
+                    ar = f2fmas(pi, tp.w, ar);
+                    ai = f2fmas(pq, tp.w, ai);
                     v[r] = {ar, ai};
                 }
                 // ---- stage A ------------------------------------------------
@@ -218,12 +248,23 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             }
             // all threads have consumed ring slot `slot` (and last frame's X2 reads are done)
             __syncthreads();
-            if (t == 0 && j + RING < n_ing) {
-                mbar_expect_tx(&sm.mbar[slot], 2 * FRAME_BYTES);
-                tma_load_1d(&sm.raw[slot][0][0], b0 + (long long)(fi + RING) * FRAME_BYTES, FRAME_BYTES,
-                            &sm.mbar[slot]);
-                tma_load_1d(&sm.raw[slot][1][0], b1 + (long long)(fi + RING) * FRAME_BYTES, FRAME_BYTES,
-                            &sm.mbar[slot]);
+            if (t == 0) {
+                // refill the slot just consumed with the ingest item RING ahead (possibly of the next segment)
+                const int jn = j + RING;
+                const uint8_t *s0 = nullptr, *s1 = nullptr;
+                if (jn < n_ing) {
+                    s0 = b0 + (long long)(g0 + jn) * FRAME_BYTES;
+                    s1 = b1 + (long long)(g0 + jn) * FRAME_BYTES;
+                } else if (jn - n_ing < n_ing_next) {
+                    s0 = nb0 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
+                    s1 = nb1 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
+                    already = jn - n_ing + 1;
+                }
+                if (s0) {
+                    mbar_expect_tx(&sm.mbar[slot], 2 * FRAME_BYTES);
+                    tma_load_1d(&sm.raw[slot][0][0], s0, FRAME_BYTES, &sm.mbar[slot]);
+                    tma_load_1d(&sm.raw[slot][1][0], s1, FRAME_BYTES, &sm.mbar[slot]);
+                }
             }
             // rotate FIR history
 #pragma unroll
@@ -235,42 +276,65 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             if (!compute) continue;
 
             // ---- exchange 1: X[k1*256 + t] --------------------------------
+            // register position 4g+b holds k1 = g + 4b; twiddles are fetched one group ahead
+            {
+                float2 tw[4], twn[4];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const int k1 = perm16(jj);
-                C2 z = v[jj];
-                if (k1 != 0) {
-                    const float2 w = sm.twA[k1][t];
-                    z = cmuls(z, w.x, w.y);
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twA[4 * b][t];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < 3) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twA[g + 1 + 4 * b][t];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k1 = g + 4 * b;
+                        C2 z = v[4 * g + b];
+                        if (k1 != 0) z = cmuls(z, tw[b].x, tw[b].y);
+                        sm.Xr[k1 * NT + t] = z.r;
+                        sm.Xi[k1 * NT + t] = z.i;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
                 }
-                sm.X[k1 * NT + t] = make_float4(z.r.x, z.r.y, z.i.x, z.i.y);
             }
             __syncthreads();
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
-                const float4 q = sm.X[k1B * 256 + n2 * 16 + lo];
-                v[n2] = {f2(q.x, q.y), f2(q.z, q.w)};
+                v[n2] = {sm.Xr[k1B * 256 + n2 * 16 + lo], sm.Xi[k1B * 256 + n2 * 16 + lo]};
             }
             // ---- stage B ---------------------------------------------------
             dft16(v);
             // exchange 2 (inside this half-warp's own 256-element region, XOR swizzle)
             // every lane of the warp must have finished reading X before anyone overwrites it
             __syncwarp();
+            {
+                float2 tw[4], twn[4];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const int k2 = perm16(jj);
-                C2 z = v[jj];
-                if (k2 != 0) {
-                    const float2 w = sm.twB[k2][lo];
-                    z = cmuls(z, w.x, w.y);
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twB[4 * b][lo];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < 3) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twB[g + 1 + 4 * b][lo];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k2 = g + 4 * b;
+                        C2 z = v[4 * g + b];
+                        if (k2 != 0) z = cmuls(z, tw[b].x, tw[b].y);
+                        sm.Xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r;
+                        sm.Xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
                 }
-                sm.X[k1B * 256 + k2 * 16 + (lo ^ k2)] = make_float4(z.r.x, z.r.y, z.i.x, z.i.y);
             }
             __syncwarp();
 #pragma unroll
             for (int n3 = 0; n3 < 16; ++n3) {
-                const float4 q = sm.X[k1B * 256 + lo * 16 + (n3 ^ lo)];
-                v[n3] = {f2(q.x, q.y), f2(q.z, q.w)};
+                v[n3] = {sm.Xr[k1B * 256 + lo * 16 + (n3 ^ lo)], sm.Xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
             }
             // ---- stage C + X-engine -----------------------------------------
             dft16(v);
@@ -283,17 +347,27 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             }
         }
 
-        // ---- segment epilogue: bins k1 + 16*k2 + 256*k3 ----------------------
-        float2 *px = prm.part_x + (long long)seg * N;
-        float2 *pa = prm.part_a + (long long)seg * N;
+        // ---- segment epilogue: bins k1 + 16*k2 + 256*k3, staged through smem so the
+        //      global writes are coalesced 16-byte stores ---------------------------
+        __syncthreads();                       // every warp is done with X (exchange-2 reads)
+        {
+            float2 *xs = sm.Xr;                                // [0,4096): cross, [4096,8192): autos (= Xi)
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            const int bin = k1B + 16 * lo + 256 * perm16(jj);
-            px[bin] = accx[jj];
-            pa[bin] = acca[jj];
+            for (int jj = 0; jj < 16; ++jj) {
+                const int bin = k1B + 16 * lo + 256 * perm16(jj);
+                xs[bin] = accx[jj];
+                xs[N + bin] = acca[jj];
+            }
+            __syncthreads();
+            float4 *px = reinterpret_cast<float4 *>(prm.part_x + (long long)seg * N);
+            float4 *pa = reinterpret_cast<float4 *>(prm.part_a + (long long)seg * N);
+#pragma unroll
+            for (int q = 0; q < N / 2 / NT; ++q) {
+                px[t + NT * q] = reinterpret_cast<const float4 *>(sm.Xr)[t + NT * q];
+                pa[t + NT * q] = reinterpret_cast<const float4 *>(sm.Xi)[t + NT * q];
+            }
+            // the next frame's exchange-1 stores wait behind the barrier at the top of its iteration
         }
-        // the next segment's first TMA may only overwrite ring slots after all
-        // threads passed the last frame's barrier, which they have.
     }
 }
 

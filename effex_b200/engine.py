@@ -116,8 +116,10 @@ class FxEngine:
 
     # ---- hot path -----------------------------------------------------------
     def process(self, iq0: torch.Tensor, iq1: torch.Tensor, n_blocks: int | None = None, autos: bool = False,
-                out=None):
-        """fx_process: one fftshifted, rot-applied cross-spectrum row per block."""
+                out=None, acc=None):
+        """fx_process: one fftshifted, rot-applied cross-spectrum row per block.
+        With `acc` (see new_accumulators) the same kernel run also adds the
+        un-normalised sums into the float64 accumulators (fx_process_acc)."""
         if n_blocks is None:
             n_blocks = iq0.numel() // (2 * self.num_samp)
         p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
@@ -128,9 +130,13 @@ class FxEngine:
         else:
             x, a0, a1 = out
         self._enter()
-        rc = self.lib.fx_process(self.h, p0, p1, n_blocks, x.data_ptr(),
-                                 a0.data_ptr() if a0 is not None else None,
-                                 a1.data_ptr() if a1 is not None else None)
+        pa0 = a0.data_ptr() if a0 is not None else None
+        pa1 = a1.data_ptr() if a1 is not None else None
+        if acc is None:
+            rc = self.lib.fx_process(self.h, p0, p1, n_blocks, x.data_ptr(), pa0, pa1)
+        else:
+            rc = self.lib.fx_process_acc(self.h, p0, p1, n_blocks, x.data_ptr(), pa0, pa1, acc["x"].data_ptr(),
+                                         acc["a0"].data_ptr(), acc["a1"].data_ptr(), acc["frames"].data_ptr())
         self._check(rc, "fx_process")
         self._exit()
         return (x, a0, a1) if autos else x

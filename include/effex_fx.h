@@ -101,6 +101,12 @@ int fx_process(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t
 int fx_integrate(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
                  double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
 
+/* fx_process_acc: fx_process and fx_integrate in one pass over the input (rows
+ * AND accumulators from the same kernel run; d_xspec may be NULL).            */
+int fx_process_acc(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                   float *d_xspec, float *d_auto0, float *d_auto1,
+                   double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
+
 /* fx_process_host: fx_process with HOST buffers (pinned or pageable): H2D of
  * the raw bytes, compute, D2H of the rows, pipelined in chunks on two
  * streams.  Synchronous.  This is the call the reference-facing wrapper

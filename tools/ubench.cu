@@ -25,6 +25,9 @@ __global__ void __launch_bounds__(512) k(float *out, long long *cyc, float s) {
             if (MODE == 3) { a[i] = __ffma2_rn(a[i], make_float2(s, s), a[(i + 1) & 7]); }   // broadcast operand
             if (MODE == 4) { p[i] = __byte_perm(p[i], 0x47000000u, 0x7414); a[i].x = __uint_as_float(p[i]) + a[i].x; }
             if (MODE == 5) { a[i] = __ffma2_rn(a[i], m, m); p[i] = __byte_perm(p[i], p[(i + 1) & 7], 0x3120); }
+            if (MODE == 6) { a[i].x = (float)(signed char)(p[i] >> 8); p[i] += (unsigned)it; }                 // I2F.S8 + IADD
+            if (MODE == 7) { a[i] = __ffma2_rn(a[i], m, m); a[(i + 4) & 7].y += (float)(signed char)(p[i] >> 16); }  // FFMA2 + I2F.S8 + FADD
+            if (MODE == 8) { a[i] = __ffma2_rn(a[i], m, make_float2((float)(signed char)(p[i] >> 16), (float)(signed char)(p[i] >> 8))); }  // FFMA2 + 2 I2F
         }
     }
     long long t1 = clock64();
@@ -58,9 +61,10 @@ int main() {
     cudaMalloc(&out, 148 * 4 * 1024 * sizeof(float));
     cudaMalloc(&cyc, 1024 * sizeof(long long));
     long long h[1024];
-    const char *names[] = {"FFMA scalar (2/iter)", "FFMA2", "FADD2", "FFMA2 bcast operand", "PRMT+FADD", "FFMA2+PRMT"};
+    const char *names[] = {"FFMA scalar (2/iter)", "FFMA2", "FADD2", "FFMA2 bcast operand", "PRMT+FADD", "FFMA2+PRMT", "I2F.S8+IADD", "FFMA2+I2F.S8+FADD", "FFMA2+2xI2F.S8"};
+    const int ninstr[] = {2, 1, 1, 1, 2, 2, 2, 3, 3};
     for (int threads : {256, 512}) {
-        for (int mode = 0; mode < 6; ++mode) {
+        for (int mode = 0; mode < 9; ++mode) {
             int grid = 148;
             switch (mode) {
                 case 0: k<0><<<grid, threads>>>(out, cyc, 1.0001f); break;
@@ -69,11 +73,14 @@ int main() {
                 case 3: k<3><<<grid, threads>>>(out, cyc, 1.0001f); break;
                 case 4: k<4><<<grid, threads>>>(out, cyc, 1.0001f); break;
                 case 5: k<5><<<grid, threads>>>(out, cyc, 1.0001f); break;
+                case 6: k<6><<<grid, threads>>>(out, cyc, 1.0001f); break;
+                case 7: k<7><<<grid, threads>>>(out, cyc, 1.0001f); break;
+                case 8: k<8><<<grid, threads>>>(out, cyc, 1.0001f); break;
             }
             cudaDeviceSynchronize();
             cudaMemcpy(h, cyc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
             double c = 0; for (int i = 0; i < grid; ++i) c += h[i]; c /= grid;
-            double instr = (double)threads / 32 * ITERS * 8 * (mode == 0 ? 2 : (mode >= 4 ? 2 : 1));
+            double instr = (double)threads / 32 * ITERS * 8 * ninstr[mode];
             printf("threads=%d %-24s cycles=%.0f  warp-instr/clk/SM=%.3f\n", threads, names[mode], c, instr / c);
         }
     }
