@@ -207,7 +207,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from effex_b200 import synth
+    from effex_b200 import synth, sharding
     from effex_b200.engine import FxEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,8 +237,7 @@ def run_ours(args):
         eng.process(d0, d1, N_BLOCKS, out=out, acc=acc)
         if world > 1:
             # the one collective of the path: reduce the small per-integration accumulators
-            flat = torch.cat([acc["x"], acc["a0"], acc["a1"], acc["frames"]])
-            dist.reduce(flat, dst=0, op=dist.ReduceOp.SUM)
+            sharding.reduce_accumulators(acc, dst=0)
             for k in acc:
                 acc[k].zero_()
 

@@ -129,7 +129,7 @@ int drain_timed(fx_handle *h) {
 int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
     const long long S = h->cfg.num_samp;
     FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, h->stream));
-    long long chunks = (S + 256 * 32 - 1) / (256 * 32);
+    long long chunks = S / 16384;          // 4 x 16-byte loads in flight per thread
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {

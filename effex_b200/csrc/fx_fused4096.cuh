@@ -39,7 +39,7 @@ struct __align__(16) Smem {
     float2 twA[16][NT];          // W4096^(t*k1), row 0 unused
     float2 twB[16][16];          // W256^(n3*k2)
     unsigned short raw[RING][2][N];   // 48 KB: (I,Q) byte pairs per channel
-    unsigned long long mbar[RING];
+    unsigned long long mbar[RING + 1];   // [RING] = tables
 };
 
 struct Segment {
@@ -134,15 +134,17 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int t = threadIdx.x;
 
-    // ---- one-time per CTA: tables to smem, mbarriers ---------------------
-    for (int p = t; p < N; p += NT) sm.taps[p] = prm.taps[p];
-    for (int q = t; q < 16 * NT; q += NT) (&sm.twA[0][0])[q] = prm.twA[q];
-    if (t < 256) (&sm.twB[0][0])[t] = prm.twB[t];
+    // ---- one-time per CTA: mbarriers, then the tables arrive by TMA bulk copy ---
     if (t == 0) {
-        for (int s = 0; s < RING; ++s) mbar_init(&sm.mbar[s], 1);
+        for (int s = 0; s <= RING; ++s) mbar_init(&sm.mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.mbar[RING], (uint32_t)(sizeof(sm.taps) + sizeof(sm.twA) + sizeof(sm.twB)));
+        tma_load_1d(&sm.taps[0], prm.taps, (uint32_t)sizeof(sm.taps), &sm.mbar[RING]);
+        tma_load_1d(&sm.twA[0][0], prm.twA, (uint32_t)sizeof(sm.twA), &sm.mbar[RING]);
+        tma_load_1d(&sm.twB[0][0], prm.twB, (uint32_t)sizeof(sm.twB), &sm.mbar[RING]);
     }
     __syncthreads();
+    bool tables_ready = false;
 
     const int k1B = t >> 4;    // after exchange 1: k1
     const int lo = t & 15;     // n3 (stage B) / k2 (stage C)
@@ -215,6 +217,10 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             const bool compute = fi >= sg.f0;
             C2 v[16];
             if (compute) {
+                if (!tables_ready) {
+                    mbar_wait(&sm.mbar[RING], 0);
+                    tables_ready = true;
+                }
                 // zero-history semantics of channelize_poly: frame fi sees taps k <= fi only
                 const int kmax = fi < T - 1 ? fi : T - 1;
 #pragma unroll
@@ -352,19 +358,24 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
         __syncthreads();                       // every warp is done with X (exchange-2 reads)
         {
             float2 *xs = sm.Xr;                                // [0,4096): cross, [4096,8192): autos (= Xi)
+            // element `bin` is staged at bin ^ ((bin >> 4) & 15): conflict-free for these scattered
+            // stores (lanes differ in bits 4..7 of bin) and for the linear read-out below
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const int bin = k1B + 16 * lo + 256 * perm16(jj);
-                xs[bin] = accx[jj];
-                xs[N + bin] = acca[jj];
+                const int sw = bin ^ lo;                       // (bin >> 4) & 15 == lo
+                xs[sw] = accx[jj];
+                xs[N + sw] = acca[jj];
             }
             __syncthreads();
-            float4 *px = reinterpret_cast<float4 *>(prm.part_x + (long long)seg * N);
-            float4 *pa = reinterpret_cast<float4 *>(prm.part_a + (long long)seg * N);
+            float2 *px = prm.part_x + (long long)seg * N;
+            float2 *pa = prm.part_a + (long long)seg * N;
 #pragma unroll
-            for (int q = 0; q < N / 2 / NT; ++q) {
-                px[t + NT * q] = reinterpret_cast<const float4 *>(sm.Xr)[t + NT * q];
-                pa[t + NT * q] = reinterpret_cast<const float4 *>(sm.Xi)[t + NT * q];
+            for (int q = 0; q < N / NT; ++q) {
+                const int o = t + NT * q;
+                const int sw = o ^ ((o >> 4) & 15);
+                px[o] = xs[sw];
+                pa[o] = xs[N + sw];
             }
             // the next frame's exchange-1 stores wait behind the barrier at the top of its iteration
         }
