@@ -10,6 +10,7 @@
 #include "../../include/effex_fx.h"
 #include "fx_common.cuh"
 #include "fx_fused4096.cuh"
+#include "fx_fused4096s.cuh"
 #include "fx_generic.cuh"
 
 namespace {
@@ -28,6 +29,7 @@ struct fx_handle {
     int logN = 0;
     int num_sms = 148;
     bool fused = false;
+    bool staggered = false;   // fused path uses fused_kernel_stag
     bool taps_set = false;
     cudaStream_t stream = nullptr, stream_copy = nullptr;
 
@@ -43,11 +45,13 @@ struct fx_handle {
     unsigned long long *d_sums = nullptr;     // [max_blocks][2][2]
     float2 *d_part_x = nullptr, *d_part_a = nullptr;
     size_t part_cap = 0;                      // in segments
-    fx::fused4096::Segment *d_segs = nullptr;
-    size_t segs_cap = 0;
+    int *d_plan = nullptr;                     // [segments x4 | cta_first | blk_first]
+    size_t segs_cap = 0, off_cta = 0, off_blk = 0;
     std::vector<fx::fused4096::Segment> h_segs;
+    std::vector<int> h_cta_first, h_blk_first;
     long long planned_blocks = -1;
-    int planned_splits = 0;
+    int plan_grid = 0;
+    bool parts_per_block = false;              // generic path: one partial per block
 
     float2 *d_g0 = nullptr, *d_g1 = nullptr, *d_gtmp = nullptr;   // generic-path frame buffers
     size_t g_cap = 0;                                             // elements per buffer
@@ -156,49 +160,55 @@ int ensure_parts(fx_handle *h, size_t n_segs) {
     return FX_OK;
 }
 
-// Choose how many segments each block is cut into so that the persistent grid
-// (one CTA per SM) finishes in the fewest frame-times.
+// Balanced contiguous partition: the n_blocks*P frames of the call are cut into `grid` equal
+// contiguous runs, one per persistent CTA; a run is a list of segments (pieces of blocks).  Only
+// the first segment of a run starts inside a block (and has to re-ingest T-1 frames of history).
 int plan_segments(fx_handle *h, long long n_blocks) {
     if (h->planned_blocks == n_blocks) return FX_OK;
-    const int P = h->P;
-    int best_s = 1;
-    double best_cost = 1e300;
-    for (int s = 1; s <= P; s *= 2) {
-        const int len = (P + s - 1) / s;
-        if (s > 1 && len < 2) break;
-        const long long nseg = n_blocks * ((P + len - 1) / len);
-        const long long waves = (nseg + h->num_sms - 1) / h->num_sms;
-        const double cost = (double)waves * (len + 0.6);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
-    }
-    const int len = (P + best_s - 1) / best_s;
-    const int splits = (P + len - 1) / len;
+    const long long P = h->P, F = n_blocks * P;
+    long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
     h->h_segs.clear();
-    h->h_segs.reserve((size_t)n_blocks * splits);
-    for (long long b = 0; b < n_blocks; ++b)
-        for (int s = 0; s < splits; ++s) {
+    h->h_cta_first.assign((size_t)grid + 1, 0);
+    h->h_blk_first.assign((size_t)n_blocks + 1, 0);
+    for (long long c = 0; c < grid; ++c) {
+        long long f = c * F / grid;
+        const long long hi = (c + 1) * F / grid;
+        h->h_cta_first[c] = (int)h->h_segs.size();
+        while (f < hi) {
             fx::fused4096::Segment sg;
-            sg.block = (int)b;
-            sg.f0 = s * len;
-            sg.nf = std::min(len, P - s * len);
+            sg.block = (int)(f / P);
+            sg.f0 = (int)(f % P);
+            sg.nf = (int)std::min<long long>(P - sg.f0, hi - f);
             sg.pad = 0;
+            if (sg.f0 == 0) h->h_blk_first[sg.block] = (int)h->h_segs.size();
             h->h_segs.push_back(sg);
+            f += sg.nf;
         }
-    if (h->h_segs.size() > h->segs_cap) {
-        if (h->d_segs) cudaFree(h->d_segs);
-        h->d_segs = nullptr;
-        h->segs_cap = 0;
-        FX_CUDA(h, cudaMalloc(&h->d_segs, h->h_segs.size() * sizeof(fx::fused4096::Segment)));
-        h->segs_cap = h->h_segs.size();
     }
-    // synchronous copy: h_segs may be rebuilt by the next call before an async copy is consumed
+    h->h_cta_first[grid] = (int)h->h_segs.size();
+    h->h_blk_first[n_blocks] = (int)h->h_segs.size();
+    h->plan_grid = (int)grid;
+    const size_t n_int = h->h_segs.size() * 4 + h->h_cta_first.size() + h->h_blk_first.size();
+    if (n_int > h->segs_cap) {
+        if (h->d_plan) cudaFree(h->d_plan);
+        h->d_plan = nullptr;
+        h->segs_cap = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_plan, n_int * sizeof(int)));
+        h->segs_cap = n_int;
+    }
+    std::vector<int> flat(n_int);
+    memcpy(flat.data(), h->h_segs.data(), h->h_segs.size() * sizeof(fx::fused4096::Segment));
+    size_t off = h->h_segs.size() * 4;
+    h->off_cta = off;
+    memcpy(flat.data() + off, h->h_cta_first.data(), h->h_cta_first.size() * sizeof(int));
+    off += h->h_cta_first.size();
+    h->off_blk = off;
+    memcpy(flat.data() + off, h->h_blk_first.data(), h->h_blk_first.size() * sizeof(int));
+    // synchronous copy: the host vectors may be rebuilt by the next call before an async copy is consumed
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
-    FX_CUDA(h, cudaMemcpy(h->d_segs, h->h_segs.data(), h->h_segs.size() * sizeof(fx::fused4096::Segment),
-                          cudaMemcpyHostToDevice));
+    FX_CUDA(h, cudaMemcpy(h->d_plan, flat.data(), n_int * sizeof(int), cudaMemcpyHostToDevice));
     h->planned_blocks = n_blocks;
-    h->planned_splits = splits;
-    int rc = ensure_parts(h, h->h_segs.size());
-    return rc;
+    return ensure_parts(h, h->h_segs.size());
 }
 
 // fused path: sums -> fused kernel -> partial sums [n_blocks*splits][N]
@@ -210,13 +220,18 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long lon
     fx::fused4096::Params prm;
     prm.iq0 = d_iq0; prm.iq1 = d_iq1; prm.sums = h->d_sums;
     prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB;
-    prm.segs = h->d_segs; prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
+    prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
+    prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
     prm.S = h->cfg.num_samp; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
-    const int grid = std::min<int>(prm.n_segs, h->num_sms);
+    const int grid = h->plan_grid;
+    h->parts_per_block = false;
     EventPair ep{};
     rc = begin_timed(h, ep);
     if (rc) return rc;
-    fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
+    if (h->staggered)
+        fx::fused4096::fused_kernel_stag<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::SmemS), h->stream>>>(prm);
+    else
+        fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
     FX_LAUNCH_CHECK(h, "fused4096");
     return end_timed(h, ep);
 }
@@ -320,8 +335,7 @@ int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long l
         rc = run_generic_chunk(h, d_iq0, d_iq1, b0, std::min(chunk, n_blocks - b0));
         if (rc) return rc;
     }
-    h->planned_splits = 1;
-    h->planned_blocks = -1;
+    h->parts_per_block = true;
     return FX_OK;
 }
 
@@ -350,7 +364,7 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     if (rc) return rc;
     const int N = h->cfg.nbins;
     if (d_acc_x) {
-        const int n_segs = (int)(n_blocks * h->planned_splits);
+        const int n_segs = h->parts_per_block ? (int)n_blocks : (int)h->h_segs.size();
         fx::generic::integrate_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(
             h->d_part_x, h->d_part_a, N, n_segs, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
         FX_LAUNCH_CHECK(h, "integrate");
@@ -361,9 +375,8 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
         const long long nb = std::min<long long>(65535, n_blocks - b0);
         grid.y = (unsigned)nb;
         fx::generic::finalize_rows_kernel<<<grid, 256, 0, h->stream>>>(
-            h->d_part_x + b0 * h->planned_splits * N, h->d_part_a + b0 * h->planned_splits * N, N, h->planned_splits,
-            1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec) + b0 * N,
-            d_auto0 ? d_auto0 + b0 * N : nullptr, d_auto1 ? d_auto1 + b0 * N : nullptr);
+            h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)b0,
+            1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0, d_auto1);
         FX_LAUNCH_CHECK(h, "finalize_rows");
     }
     return FX_OK;
@@ -530,6 +543,9 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         CREATE_CUDA(cudaMemcpy(h->d_twB, twB.data(), twB.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::fused4096::Smem)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel_stag, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(fx::fused4096::SmemS)));
+        h->staggered = !(cfg->flags & FX_FLAG_LOCKSTEP_KERNEL);
     }
 #undef CREATE_CUDA
     *out = h;
@@ -543,7 +559,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums, h->d_part_x,
-                    h->d_part_a, h->d_segs, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_plan, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

@@ -55,7 +55,8 @@ struct Params {
     const float4 *taps;                 // [N]
     const float2 *twA;                  // [16][256]
     const float2 *twB;                  // [16][16]
-    const Segment *segs;
+    const Segment *segs;                // all segments, in global frame order
+    const int *cta_first;               // [gridDim.x + 1]: CTA c walks segs[cta_first[c] .. cta_first[c+1])
     float2 *part_x;                     // [n_segs][N] sum F0*conj(F1) (natural bin order)
     float2 *part_a;                     // [n_segs][N] (sum|F0|^2, sum|F1|^2)
     long long S;                        // samples per block
@@ -124,6 +125,15 @@ __device__ __forceinline__ void unpack_pairs(uint32_t w, float2 &pi, float2 &pq)
         pq = f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg);
     }
 }
+#ifndef FX_EXP_NOTAPLDS
+#define FX_EXP_NOTAPLDS 0   // experiment: taps from a register instead of smem (WRONG results)
+#endif
+#ifndef FX_EXP_NOTWLDS
+#define FX_EXP_NOTWLDS 0    // experiment: twiddles from registers instead of smem (WRONG results)
+#endif
+#ifndef FX_EXP_NOX
+#define FX_EXP_NOX 0        // experiment: skip the exchange loads/stores (WRONG results)
+#endif
 #ifndef FX_I2F_TAPS
 #define FX_I2F_TAPS 0
 #endif
@@ -151,7 +161,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
     uint32_t ring_cnt = 0;     // ingest counter: slot = cnt % RING, parity = (cnt / RING) & 1
 
     int already = 0;           // ingest items of the coming segment already issued by the previous one (thread 0)
-    for (int seg = blockIdx.x; seg < prm.n_segs; seg += gridDim.x) {
+    const int seg_end = prm.cta_first[blockIdx.x + 1];
+    for (int seg = prm.cta_first[blockIdx.x]; seg < seg_end; ++seg) {
         const Segment sg = prm.segs[seg];
         const uint8_t *b0 = prm.iq0 + 2ll * prm.S * sg.block;
         const uint8_t *b1 = prm.iq1 + 2ll * prm.S * sg.block;
@@ -172,8 +183,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
         const int g0 = sg.f0 - (T - 1) > 0 ? sg.f0 - (T - 1) : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
         // the segment after this one (same CTA): its first frames are prefetched during our last ones
-        const int nseg = seg + gridDim.x;
-        const bool have_next = nseg < prm.n_segs && n_ing >= RING;
+        const int nseg = seg + 1;
+        const bool have_next = nseg < seg_end && n_ing >= RING;
         Segment ng = sg;
         if (have_next) ng = prm.segs[nseg];
         const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
                 const int kmax = fi < T - 1 ? fi : T - 1;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    float4 tp = sm.taps[t + NT * r];
+                    float4 tp = FX_EXP_NOTAPLDS ? make_float4(nmI.x, nmI.y, nmQ.x, 1e-3f * r) : sm.taps[t + NT * r];
                     if (kmax < T - 1) {
                         tp.w = 0.f;
                         if (kmax < 2) tp.z = 0.f;
@@ -286,20 +297,19 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             {
                 float2 tw[4], twn[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = sm.twA[4 * b][t];
+                for (int b = 0; b < 4; ++b) tw[b] = FX_EXP_NOTWLDS ? f2(nmI.x, nmQ.y) : sm.twA[4 * b][t];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = sm.twA[g + 1 + 4 * b][t];
+                        for (int b = 0; b < 4; ++b) twn[b] = FX_EXP_NOTWLDS ? f2(nmI.y, nmQ.x) : sm.twA[g + 1 + 4 * b][t];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k1 = g + 4 * b;
                         C2 z = v[4 * g + b];
                         if (k1 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        sm.Xr[k1 * NT + t] = z.r;
-                        sm.Xi[k1 * NT + t] = z.i;
+                        if (!FX_EXP_NOX) { sm.Xr[k1 * NT + t] = z.r; sm.Xi[k1 * NT + t] = z.i; } else v[4 * g + b] = z;
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tw[b] = twn[b];
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             __syncthreads();
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
-                v[n2] = {sm.Xr[k1B * 256 + n2 * 16 + lo], sm.Xi[k1B * 256 + n2 * 16 + lo]};
+                if (!FX_EXP_NOX) v[n2] = {sm.Xr[k1B * 256 + n2 * 16 + lo], sm.Xi[k1B * 256 + n2 * 16 + lo]};
             }
             // ---- stage B ---------------------------------------------------
             dft16(v);
@@ -318,20 +328,19 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             {
                 float2 tw[4], twn[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = sm.twB[4 * b][lo];
+                for (int b = 0; b < 4; ++b) tw[b] = FX_EXP_NOTWLDS ? f2(nmI.x, nmQ.y) : sm.twB[4 * b][lo];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = sm.twB[g + 1 + 4 * b][lo];
+                        for (int b = 0; b < 4; ++b) twn[b] = FX_EXP_NOTWLDS ? f2(nmI.y, nmQ.x) : sm.twB[g + 1 + 4 * b][lo];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k2 = g + 4 * b;
                         C2 z = v[4 * g + b];
                         if (k2 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        sm.Xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r;
-                        sm.Xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i;
+                        if (!FX_EXP_NOX) { sm.Xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r; sm.Xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i; } else v[4 * g + b] = z;
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tw[b] = twn[b];
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             __syncwarp();
 #pragma unroll
             for (int n3 = 0; n3 < 16; ++n3) {
-                v[n3] = {sm.Xr[k1B * 256 + lo * 16 + (n3 ^ lo)], sm.Xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
+                if (!FX_EXP_NOX) v[n3] = {sm.Xr[k1B * 256 + lo * 16 + (n3 ^ lo)], sm.Xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
             }
             // ---- stage C + X-engine -----------------------------------------
             dft16(v);

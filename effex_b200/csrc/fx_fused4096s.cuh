@@ -1,0 +1,371 @@
+// fx_fused4096s.cuh -- staggered variant of the fused kernel (same math, same thread/point/bin
+// mapping as fx_fused4096.cuh; see that file for the dataflow).
+//
+// Why: in fused_kernel all 8 warps run the same phase at the same time, so the shared-memory
+// bursts of the two exchanges and the FMA-heavy butterflies/FIR never overlap (measured: time ~
+// compute-only time + exchange time).  Here the CTA is split into two warp groups that do the
+// two halves of a frame's work in OPPOSITE order:
+//     group 0 (warps 0-3):  FIR + stage A of frame q+1   then   stages B, C + X-engine of frame q
+//     group 1 (warps 4-7):  stages B, C + X-engine of q  then   FIR + stage A of frame q+1
+// Every scheduler holds one warp of each group (warp w and w+4), so at any time it has one
+// ALU/FMA-heavy FIR warp and one exchange-heavy FFT warp to pick from.  Exchange 1 is double
+// buffered (frame q+1 is written while frame q is read), which also removes one of the two CTA
+// barriers per frame.  The FIR taps live in TENSOR MEMORY (each thread's 64 taps are private to
+// it: tcgen05.st once, tcgen05.ld per frame) because the second exchange buffer takes the shared
+// memory they used to occupy.
+#pragma once
+#include "fx_fused4096.cuh"
+
+namespace fx {
+namespace fused4096 {
+
+#ifndef FX_STAG_DUP
+#define FX_STAG_DUP 0
+#endif
+#ifndef FX_STAG_TAPS
+#define FX_STAG_TAPS 2     // 0: fake taps (timing experiments only, WRONG results), 2: tensor memory
+#endif
+constexpr int RING_S = 2;
+
+struct __align__(16) SmemS {
+    float2 Xr[2][N];             // 2 x 32 KB exchange planes (re ch0, re ch1), double buffered
+    float2 Xi[2][N];             // 2 x 32 KB exchange planes (im ch0, im ch1)
+    float2 twA[16][NT];          // W4096^(t*k1)
+    float2 twB[16][16];          // W256^(n3*k2)
+    unsigned short raw[RING_S][2][N];
+    unsigned long long mbar[RING_S + 1];
+    uint32_t tmem_base;
+};
+
+// ---- tensor memory helpers (tcgen05; 32 lanes x 32-bit columns per warp quarter) -------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w))
+                 : "memory");
+}
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "r"(taddr));
+    return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+}
+// the loaded registers are routed through the wait so that no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b, float4 &c, float4 &d) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "+f"(c.x),
+                   "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w)::"memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemS &sm = *reinterpret_cast<SmemS *>(smem_raw);
+    const int t = threadIdx.x;
+    const int warp = t >> 5;
+    const int grp = warp >> 2;          // 0: FIR first, 1: FFT first
+
+    if (t == 0) {
+        for (int s = 0; s <= RING_S; ++s) mbar_init(&sm.mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.mbar[RING_S], (uint32_t)(sizeof(sm.twA) + sizeof(sm.twB)));
+        tma_load_1d(&sm.twA[0][0], prm.twA, (uint32_t)sizeof(sm.twA), &sm.mbar[RING_S]);
+        tma_load_1d(&sm.twB[0][0], prm.twB, (uint32_t)sizeof(sm.twB), &sm.mbar[RING_S]);
+    }
+#if FX_STAG_TAPS == 2
+    // 128 columns: warps w and w+4 share a lane quarter, 64 columns (16 points x 4 taps) each
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 128);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#endif
+    __syncthreads();
+#if FX_STAG_TAPS == 2
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_taps = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * grp);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) tmem_st4(tm_taps + 4 * r, prm.taps[t + NT * r]);
+    tmem_wait_st();
+#endif
+    bool tables_ready = false;
+
+    const int k1B = t >> 4;
+    const int lo = t & 15;
+    uint32_t ring_cnt = 0;
+    int already = 0;
+
+    const int seg_end = prm.cta_first[blockIdx.x + 1];
+    for (int seg = prm.cta_first[blockIdx.x]; seg < seg_end; ++seg) {
+        const Segment sg = prm.segs[seg];
+        const uint8_t *b0 = prm.iq0 + 2ll * prm.S * sg.block;
+        const uint8_t *b1 = prm.iq1 + 2ll * prm.S * sg.block;
+        float2 nmI, nmQ;
+        if (prm.dc_remove) {
+            const unsigned long long *su = prm.sums + 4ll * sg.block;
+            const double inv = 1.0 / (double)prm.S;
+            nmI = f2((float)(128.0 - (double)su[0] * inv), (float)(128.0 - (double)su[2] * inv));
+            nmQ = f2((float)(128.0 - (double)su[1] * inv), (float)(128.0 - (double)su[3] * inv));
+        } else {
+            nmI = f2(0.5f, 0.5f);
+            nmQ = f2(0.5f, 0.5f);
+        }
+        const int g0 = sg.f0 - (T - 1) > 0 ? sg.f0 - (T - 1) : 0;
+        const int n_ing = sg.f0 + sg.nf - g0;
+        const int nseg = seg + 1;
+        const bool have_next = nseg < seg_end && n_ing >= RING_S;
+        Segment ng = sg;
+        if (have_next) ng = prm.segs[nseg];
+        const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
+        const int n_ing_next = have_next ? ng.f0 + ng.nf - ng0 : 0;
+        const uint8_t *nb0 = prm.iq0 + 2ll * prm.S * ng.block;
+        const uint8_t *nb1 = prm.iq1 + 2ll * prm.S * ng.block;
+        if (t == 0) {
+            const int pre = n_ing < RING_S ? n_ing : RING_S;
+            for (int j = already; j < pre; ++j) {
+                const uint32_t s = (ring_cnt + j) % RING_S;
+                mbar_expect_tx(&sm.mbar[s], 2 * FRAME_BYTES);
+                tma_load_1d(&sm.raw[s][0][0], b0 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][1][0], b1 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+            }
+            already = 0;
+        }
+        // refill of the ring slot used by ingest item j (called by thread 0 after the barrier that
+        // follows every group's reads of that slot)
+        auto refill = [&](int j, uint32_t slot) {
+            const int jn = j + RING_S;
+            const uint8_t *s0 = nullptr, *s1 = nullptr;
+            if (jn < n_ing) {
+                s0 = b0 + (long long)(g0 + jn) * FRAME_BYTES;
+                s1 = b1 + (long long)(g0 + jn) * FRAME_BYTES;
+            } else if (jn - n_ing < n_ing_next) {
+                s0 = nb0 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
+                s1 = nb1 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
+                already = jn - n_ing + 1;
+            }
+            if (s0) {
+                mbar_expect_tx(&sm.mbar[slot], 2 * FRAME_BYTES);
+                tma_load_1d(&sm.raw[slot][0][0], s0, FRAME_BYTES, &sm.mbar[slot]);
+                tma_load_1d(&sm.raw[slot][1][0], s1, FRAME_BYTES, &sm.mbar[slot]);
+            }
+        };
+
+        uint32_t hist[T - 1][16];
+        float2 accx[16], acca[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            accx[j] = f2(0.f, 0.f);
+            acca[j] = f2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < T - 1; ++k) hist[k][j] = 0u;
+        }
+        C2 v[16];
+
+        // ---- ingest item j: raw -> history; if `compute`, FIR + stage A -> exchange buffer `buf` ----
+        auto fir_stage_a = [&](int j, bool compute, int buf) {
+            const int fi = g0 + j;
+            const uint32_t cnt = ring_cnt + (uint32_t)j;          // ring_cnt = counter at segment start
+            const uint32_t slot = cnt % RING_S;
+            mbar_wait(&sm.mbar[slot], (cnt / RING_S) & 1u);
+            uint32_t cur[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t a = sm.raw[slot][0][t + NT * r];
+                const uint32_t b = sm.raw[slot][1][t + NT * r];
+                cur[r] = __byte_perm(a, b, 0x5410);
+            }
+            if (compute) {
+                if (!tables_ready) {
+                    mbar_wait(&sm.mbar[RING_S], 0);
+                    tables_ready = true;
+                }
+                const int kmax = fi < T - 1 ? fi : T - 1;
+                float4 tq[4];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    float4 tp;
+#if FX_STAG_TAPS == 2
+                    if ((r & 3) == 0) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) tq[u] = tmem_ld4(tm_taps + 4 * (r + u));
+                        tmem_wait_ld(tq[0], tq[1], tq[2], tq[3]);
+                    }
+                    tp = tq[r & 3];
+#else
+                    tp = make_float4(nmI.x, nmI.y, nmQ.x, 1e-3f * r);
+#endif
+                    if (kmax < T - 1) {
+                        tp.w = 0.f;
+                        if (kmax < 2) tp.z = 0.f;
+                        if (kmax < 1) tp.y = 0.f;
+                    }
+                    const float hs = (tp.x + tp.y) + (tp.z + tp.w);
+                    float2 ar = f2muls(nmI, hs);
+                    float2 ai = f2muls(nmQ, hs);
+                    float2 pi, pq;
+                    unpack_pairs<false>(cur[r], pi, pq);
+                    ar = f2fmas(pi, tp.x, ar);
+                    ai = f2fmas(pq, tp.x, ai);
+                    unpack_pairs<false>(hist[0][r], pi, pq);
+                    ar = f2fmas(pi, tp.y, ar);
+                    ai = f2fmas(pq, tp.y, ai);
+                    unpack_pairs<false>(hist[1][r], pi, pq);
+                    ar = f2fmas(pi, tp.z, ar);
+                    ai = f2fmas(pq, tp.z, ai);
+                    unpack_pairs<false>(hist[2][r], pi, pq);
+                    ar = f2fmas(pi, tp.w, ar);
+                    ai = f2fmas(pq, tp.w, ai);
+                    v[r] = {ar, ai};
+                }
+                dft16(v);
+                float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
+                float2 tw[4], twn[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twA[4 * b][t];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < 3) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twA[g + 1 + 4 * b][t];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k1 = g + 4 * b;
+                        C2 z = v[4 * g + b];
+                        if (k1 != 0) z = cmuls(z, tw[b].x, tw[b].y);
+                        xr[k1 * NT + t] = z.r;
+                        xi[k1 * NT + t] = z.i;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                hist[2][r] = hist[1][r];
+                hist[1][r] = hist[0][r];
+                hist[0][r] = cur[r];
+            }
+        };
+
+        // ---- stages B, C and the X-engine of the frame held in exchange buffer `buf` ---------------
+        auto fft_rest = [&](int buf) {
+            float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = {xr[k1B * 256 + n2 * 16 + lo], xi[k1B * 256 + n2 * 16 + lo]};
+            dft16(v);
+            __syncwarp();
+            {
+                float2 tw[4], twn[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twB[4 * b][lo];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < 3) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twB[g + 1 + 4 * b][lo];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k2 = g + 4 * b;
+                        C2 z = v[4 * g + b];
+                        if (k2 != 0) z = cmuls(z, tw[b].x, tw[b].y);
+                        xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r;
+                        xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = {xr[k1B * 256 + lo * 16 + (n3 ^ lo)], xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
+            dft16(v);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
+                accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
+                accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
+                acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+            }
+        };
+
+        // step s: FIR/stage A of ingest item s (history-only while s < j0) and stages B, C + X-engine of
+        // the frame whose stage A finished in step s-1, in group-dependent order; one CTA barrier per step
+        const int j0 = sg.f0 - g0;
+#if FX_STAG_DUP
+        // two copies of the step loop, one per group: no control-flow merges inside a step
+        if (grp == 0) {
+#pragma unroll 1
+            for (int s = 0; s <= n_ing; ++s) {
+                const int q = s - j0 - 1;
+                if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
+                if (q >= 0) fft_rest(q & 1);
+                __syncthreads();
+                if (t == 0 && s < n_ing) refill(s, (ring_cnt + (uint32_t)s) % RING_S);
+            }
+        } else {
+#pragma unroll 1
+            for (int s = 0; s <= n_ing; ++s) {
+                const int q = s - j0 - 1;
+                if (q >= 0) fft_rest(q & 1);
+                if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
+                __syncthreads();
+            }
+        }
+#else
+#pragma unroll 1
+        for (int s = 0; s <= n_ing; ++s) {
+            const int q = s - j0 - 1;                 // frame (segment-relative) whose exchange buffer is ready
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (half == grp) {
+                    if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
+                } else {
+                    if (q >= 0) fft_rest(q & 1);
+                }
+            }
+            __syncthreads();
+            if (t == 0 && s < n_ing) refill(s, (ring_cnt + (uint32_t)s) % RING_S);
+        }
+#endif
+        ring_cnt += (uint32_t)n_ing;
+
+        // ---- segment epilogue (both exchange buffers are free after the last barrier) ----------------
+        {
+            float2 *xs = &sm.Xr[0][0];                          // cross in Xr[0], autos in Xr[1]
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int bin = k1B + 16 * lo + 256 * perm16(jj);
+                const int sw = bin ^ lo;
+                xs[sw] = accx[jj];
+                xs[N + sw] = acca[jj];
+            }
+            __syncthreads();
+            float2 *px = prm.part_x + (long long)seg * N;
+            float2 *pa = prm.part_a + (long long)seg * N;
+#pragma unroll
+            for (int q = 0; q < N / NT; ++q) {
+                const int o = t + NT * q;
+                const int sw = o ^ ((o >> 4) & 15);
+                px[o] = xs[sw];
+                pa[o] = xs[N + sw];
+            }
+            __syncthreads();       // the next segment's first exchange stores must not overtake these reads
+        }
+    }
+#if FX_STAG_TAPS == 2
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(sm.tmem_base, 128);
+#endif
+}
+
+}  // namespace fused4096
+}  // namespace fx

@@ -202,21 +202,25 @@ __global__ void __launch_bounds__(256) xengine_kernel(const float2 *__restrict__
 
 // ---------------------------------------------------------------------------
 // finalize: rows in the reference's output order (effex.py:519-521):
-//   out[b][j] = conj(rot[c]) * (1/P) * sum_seg part_x[b*splits+seg][c],  c = (j + N/2) mod N
+//   out[b][j] = conj(rot[c]) * (1/P) * sum_{s in segments of block b} part_x[s][c],  c = (j + N/2) mod N
+// blk_first[b] .. blk_first[b+1] are block b's segments (NULL: one segment per block, s = b).
 // grid = (ceil(N/256), n_blocks)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__restrict__ part_x,
-                                                            const float2 *__restrict__ part_a, int N, int splits,
+                                                            const float2 *__restrict__ part_a, int N,
+                                                            const int *__restrict__ blk_first, int block0,
                                                             float inv_frames, const float2 *__restrict__ rot,
                                                             float2 *__restrict__ xspec, float *__restrict__ auto0,
                                                             float *__restrict__ auto1) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = block0 + blockIdx.y;
     if (j >= N) return;
     const int c = (j + (N >> 1)) & (N - 1);
+    const int s0 = blk_first ? blk_first[b] : b;
+    const int s1 = blk_first ? blk_first[b + 1] : b + 1;
     float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const long long o = ((long long)b * splits + s) * N + c;
+    for (int s = s0; s < s1; ++s) {
+        const long long o = (long long)s * N + c;
         const float2 x = part_x[o];
         const float2 a = part_a[o];
         xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;

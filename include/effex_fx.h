@@ -60,6 +60,7 @@ typedef struct {
 } fx_config;
 
 #define FX_FLAG_FORCE_GENERIC 1   /* never take the fused kernels (used to cross-check them) */
+#define FX_FLAG_LOCKSTEP_KERNEL 2 /* fused path: use the simpler lock-step kernel instead of the staggered one */
 
 /* ---- lifetime --------------------------------------------------------- */
 int fx_abi_version(void);

@@ -89,19 +89,23 @@ def test_fused_equals_generic_path(c1):
 
 @pytest.mark.parametrize("nb", [1, 2, 5, 149, 300])
 def test_fused_segment_plans_agree(c1, nb):
-    """Every block count picks its own split of blocks into segments; rows must not
-    depend on it.  Input = 2 distinct blocks tiled."""
+    """Every block count gets its own partition of the frames into per-CTA segments; rows must not
+    depend on it beyond float32 summation order, and a repeated call must be bit-identical.
+    Input = 2 distinct blocks tiled."""
     S, N = c1["S"], c1["N"]
     base0, base1 = c1["raw0"][:4 * S], c1["raw1"][:4 * S]
     raw0 = np.tile(base0, (nb + 1) // 2)[:2 * S * nb]
     raw1 = np.tile(base1, (nb + 1) // 2)[:2 * S * nb]
     eng = FxEngine(S, N, 4, max_blocks=nb)
-    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    d0, d1 = dev(raw0), dev(raw1)
+    x = eng.process(d0, d1, nb).cpu().numpy()
     ref = oracle_rows(base0, base1, S, N, 2.4e6, 1.4204e9, 0.0, min(nb, 2))
     for b in range(nb):
         assert_close(x[b], ref[b % 2], what=f"nb={nb} block {b}")
-        if b >= 2:      # identical input blocks -> bit-identical rows, whatever CTA took them
-            np.testing.assert_array_equal(x[b], x[b - 2])
+        if b >= 2:      # identical input blocks, cut into segments at different frames
+            assert_close(x[b], x[b - 2], tol=2e-6, what=f"nb={nb} block {b} vs {b - 2}")
+    again = eng.process(d0, d1, nb).cpu().numpy()
+    np.testing.assert_array_equal(x, again)         # deterministic: no atomics on the data path
     eng.close()
 
 
