@@ -13,12 +13,25 @@
 // barriers per frame.  The FIR taps live in TENSOR MEMORY (each thread's 64 taps are private to
 // it: tcgen05.st once, tcgen05.ld per frame) because the second exchange buffer takes the shared
 // memory they used to occupy.
+//
+// The FIR runs in TRANSPOSED form: each incoming sample is unpacked ONCE and scattered into the
+// partial sums of the four frames it contributes to,
+//     out_i = t0*y_i + z1 ;  z1' = t1*y_i + z2 ;  z2' = t2*y_i + z3 ;  z3' = t3*y_i
+// (identical arithmetic to the direct form up to float32 summation order; zero state at a block
+// start IS channelize_poly's zero history).  The state z1..z3 (12 floats per point, 48 KB/warp pair)
+// is thread-private, so it lives in tensor memory next to the taps: one tcgen05.ld.x16 and one
+// tcgen05.st.x8 + .x4 per point per frame (measured tcgen05.ld 2.6 KB/clk/SM, tcgen05.st
+// 285 B/clk/SM, tools/ubench_tmem.cu).  Compared with re-unpacking the three history frames this
+// removes 12 of 16 PRMT and 4 of 8 FADD2 per point and the 48 history registers.
 #pragma once
 #include "fx_fused4096.cuh"
 
 namespace fx {
 namespace fused4096 {
 
+#ifndef FX_STAG_PREFETCH
+#define FX_STAG_PREFETCH 0
+#endif
 #ifndef FX_STAG_DUP
 #define FX_STAG_DUP 0
 #endif
@@ -66,13 +79,34 @@ __device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b, float4 &c, fl
                  : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "+f"(c.x),
                    "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w)::"memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t (&q)[16], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(taddr));
+}
+// wait for all outstanding tcgen05.ld; the registers of the load being consumed are routed through
+// the instruction so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&q)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                   "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])::"memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, float2 a, float2 b, float2 c, float2 d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(b.x)),
+                 "r"(__float_as_uint(b.y)), "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)),
+                 "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemS &sm = *reinterpret_cast<SmemS *>(smem_raw);
     const int t = threadIdx.x;
-    const int warp = t >> 5;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);   // broadcast: lets the compiler keep it (and TMEM addresses) uniform
     const int grp = warp >> 2;          // 0: FIR first, 1: FFT first
 
     if (t == 0) {
@@ -83,16 +117,17 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         tma_load_1d(&sm.twB[0][0], prm.twB, (uint32_t)sizeof(sm.twB), &sm.mbar[RING_S]);
     }
 #if FX_STAG_TAPS == 2
-    // 128 columns: warps w and w+4 share a lane quarter, 64 columns (16 points x 4 taps) each
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 128);
+    // all 512 columns: warps w and w+4 share a lane quarter, 256 columns each =
+    // 16 points x [4 taps | z1 | z2 | z3 (4 floats each: re ch0, re ch1, im ch0, im ch1)]
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #endif
     __syncthreads();
 #if FX_STAG_TAPS == 2
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tm_taps = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * grp);
+    const uint32_t tm_pts = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * grp);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) tmem_st4(tm_taps + 4 * r, prm.taps[t + NT * r]);
+    for (int r = 0; r < 16; ++r) tmem_st4(tm_pts + 16 * r, prm.taps[t + NT * r]);
     tmem_wait_st();
 #endif
     bool tables_ready = false;
@@ -157,72 +192,57 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             }
         };
 
-        uint32_t hist[T - 1][16];
         float2 accx[16], acca[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             accx[j] = f2(0.f, 0.f);
             acca[j] = f2(0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < T - 1; ++k) hist[k][j] = 0u;
         }
         C2 v[16];
+#if FX_STAG_TAPS == 2
+        // zero FIR state: a segment either starts a block (zero history is the reference's semantics)
+        // or first re-ingests the T-1 frames before its first output frame
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            tmem_st4(tm_pts + 16 * r + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            tmem_st4(tm_pts + 16 * r + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+            tmem_st4(tm_pts + 16 * r + 12, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+#endif
 
         // ---- ingest item j: raw -> history; if `compute`, FIR + stage A -> exchange buffer `buf` ----
         auto fir_stage_a = [&](int j, bool compute, int buf) {
-            const int fi = g0 + j;
             const uint32_t cnt = ring_cnt + (uint32_t)j;          // ring_cnt = counter at segment start
             const uint32_t slot = cnt % RING_S;
             mbar_wait(&sm.mbar[slot], (cnt / RING_S) & 1u);
-            uint32_t cur[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
+            tmem_wait_st();                                       // last frame's state stores have landed
+            const float2 mg = f2(-kMagic, -kMagic);
+            // one point: tp = taps, z1..z3 = state (re ch0, re ch1, im ch0, im ch1); out = t0*y + z1
+            auto point = [&](int r, const float4 &tp, const float4 &z1, const float4 &z2, const float4 &z3) {
                 const uint32_t a = sm.raw[slot][0][t + NT * r];
                 const uint32_t b = sm.raw[slot][1][t + NT * r];
-                cur[r] = __byte_perm(a, b, 0x5410);
+                const uint32_t w = __byte_perm(a, b, 0x5410);     // (I0,Q0,I1,Q1)
+                const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
+                const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
+                v[r] = {f2fmas(yr, tp.x, f2(z1.x, z1.y)), f2fmas(yi, tp.x, f2(z1.z, z1.w))};
+                const float2 n1r = f2fmas(yr, tp.y, f2(z2.x, z2.y)), n1i = f2fmas(yi, tp.y, f2(z2.z, z2.w));
+                const float2 n2r = f2fmas(yr, tp.z, f2(z3.x, z3.y)), n2i = f2fmas(yi, tp.z, f2(z3.z, z3.w));
+                const float2 n3r = f2muls(yr, tp.w), n3i = f2muls(yi, tp.w);
+                tmem_st4(tm_pts + 16 * r + 4, make_float4(n1r.x, n1r.y, n1i.x, n1i.y));
+                tmem_st4(tm_pts + 16 * r + 8, make_float4(n2r.x, n2r.y, n2i.x, n2i.y));
+                tmem_st4(tm_pts + 16 * r + 12, make_float4(n3r.x, n3r.y, n3i.x, n3i.y));
+            };
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                float4 tp = tmem_ld4(tm_pts + 16 * r), z1 = tmem_ld4(tm_pts + 16 * r + 4),
+                       z2 = tmem_ld4(tm_pts + 16 * r + 8), z3 = tmem_ld4(tm_pts + 16 * r + 12);
+                tmem_wait_ld(tp, z1, z2, z3);
+                point(r, tp, z1, z2, z3);
             }
             if (compute) {
                 if (!tables_ready) {
                     mbar_wait(&sm.mbar[RING_S], 0);
                     tables_ready = true;
-                }
-                const int kmax = fi < T - 1 ? fi : T - 1;
-                float4 tq[4];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    float4 tp;
-#if FX_STAG_TAPS == 2
-                    if ((r & 3) == 0) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) tq[u] = tmem_ld4(tm_taps + 4 * (r + u));
-                        tmem_wait_ld(tq[0], tq[1], tq[2], tq[3]);
-                    }
-                    tp = tq[r & 3];
-#else
-                    tp = make_float4(nmI.x, nmI.y, nmQ.x, 1e-3f * r);
-#endif
-                    if (kmax < T - 1) {
-                        tp.w = 0.f;
-                        if (kmax < 2) tp.z = 0.f;
-                        if (kmax < 1) tp.y = 0.f;
-                    }
-                    const float hs = (tp.x + tp.y) + (tp.z + tp.w);
-                    float2 ar = f2muls(nmI, hs);
-                    float2 ai = f2muls(nmQ, hs);
-                    float2 pi, pq;
-                    unpack_pairs<false>(cur[r], pi, pq);
-                    ar = f2fmas(pi, tp.x, ar);
-                    ai = f2fmas(pq, tp.x, ai);
-                    unpack_pairs<false>(hist[0][r], pi, pq);
-                    ar = f2fmas(pi, tp.y, ar);
-                    ai = f2fmas(pq, tp.y, ai);
-                    unpack_pairs<false>(hist[1][r], pi, pq);
-                    ar = f2fmas(pi, tp.z, ar);
-                    ai = f2fmas(pq, tp.z, ai);
-                    unpack_pairs<false>(hist[2][r], pi, pq);
-                    ar = f2fmas(pi, tp.w, ar);
-                    ai = f2fmas(pq, tp.w, ai);
-                    v[r] = {ar, ai};
                 }
                 dft16(v);
                 float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
@@ -246,12 +266,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tw[b] = twn[b];
                 }
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                hist[2][r] = hist[1][r];
-                hist[1][r] = hist[0][r];
-                hist[0][r] = cur[r];
             }
         };
 
@@ -363,7 +377,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
     }
 #if FX_STAG_TAPS == 2
     __syncthreads();
-    if (warp == 0) tmem_dealloc(sm.tmem_base, 128);
+    if (warp == 0) tmem_dealloc(sm.tmem_base, 512);
 #endif
 }
 
