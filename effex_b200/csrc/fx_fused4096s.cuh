@@ -48,6 +48,9 @@ struct __align__(16) SmemS {
     unsigned short raw[RING_S][2][N];
     unsigned long long mbar[RING_S + 1];
     uint32_t tmem_base;
+    // TMA producer state of the current segment (written and read by thread 0 only; kept out of registers)
+    const uint8_t *src0, *src1, *nsrc0, *nsrc1;
+    int n_ing, n_ing_next;
 };
 
 // ---- tensor memory helpers (tcgen05; 32 lanes x 32-bit columns per warp quarter) -------------
@@ -154,21 +157,25 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         }
         const int g0 = sg.f0 - (T - 1) > 0 ? sg.f0 - (T - 1) : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
-        const int nseg = seg + 1;
-        const bool have_next = nseg < seg_end && n_ing >= RING_S;
-        Segment ng = sg;
-        if (have_next) ng = prm.segs[nseg];
-        const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
-        const int n_ing_next = have_next ? ng.f0 + ng.nf - ng0 : 0;
-        const uint8_t *nb0 = prm.iq0 + 2ll * prm.S * ng.block;
-        const uint8_t *nb1 = prm.iq1 + 2ll * prm.S * ng.block;
         if (t == 0) {
+            // the segment after this one (same CTA): its first frames are prefetched during our last ones
+            const int nseg = seg + 1;
+            const bool have_next = nseg < seg_end && n_ing >= RING_S;
+            Segment ng = sg;
+            if (have_next) ng = prm.segs[nseg];
+            const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
+            sm.src0 = b0 + (long long)g0 * FRAME_BYTES;
+            sm.src1 = b1 + (long long)g0 * FRAME_BYTES;
+            sm.nsrc0 = prm.iq0 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
+            sm.nsrc1 = prm.iq1 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
+            sm.n_ing = n_ing;
+            sm.n_ing_next = have_next ? ng.f0 + ng.nf - ng0 : 0;
             const int pre = n_ing < RING_S ? n_ing : RING_S;
             for (int j = already; j < pre; ++j) {
                 const uint32_t s = (ring_cnt + j) % RING_S;
                 mbar_expect_tx(&sm.mbar[s], 2 * FRAME_BYTES);
-                tma_load_1d(&sm.raw[s][0][0], b0 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
-                tma_load_1d(&sm.raw[s][1][0], b1 + (long long)(g0 + j) * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][0][0], sm.src0 + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][1][0], sm.src1 + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
             }
             already = 0;
         }
@@ -176,14 +183,15 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         // follows every group's reads of that slot)
         auto refill = [&](int j, uint32_t slot) {
             const int jn = j + RING_S;
+            const int ni = sm.n_ing;
             const uint8_t *s0 = nullptr, *s1 = nullptr;
-            if (jn < n_ing) {
-                s0 = b0 + (long long)(g0 + jn) * FRAME_BYTES;
-                s1 = b1 + (long long)(g0 + jn) * FRAME_BYTES;
-            } else if (jn - n_ing < n_ing_next) {
-                s0 = nb0 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
-                s1 = nb1 + (long long)(ng0 + jn - n_ing) * FRAME_BYTES;
-                already = jn - n_ing + 1;
+            if (jn < ni) {
+                s0 = sm.src0 + (long long)jn * FRAME_BYTES;
+                s1 = sm.src1 + (long long)jn * FRAME_BYTES;
+            } else if (jn - ni < sm.n_ing_next) {
+                s0 = sm.nsrc0 + (long long)(jn - ni) * FRAME_BYTES;
+                s1 = sm.nsrc1 + (long long)(jn - ni) * FRAME_BYTES;
+                already = jn - ni + 1;
             }
             if (s0) {
                 mbar_expect_tx(&sm.mbar[slot], 2 * FRAME_BYTES);
@@ -218,10 +226,16 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             tmem_wait_st();                                       // last frame's state stores have landed
             const float2 mg = f2(-kMagic, -kMagic);
             // one point: tp = taps, z1..z3 = state (re ch0, re ch1, im ch0, im ch1); out = t0*y + z1
-            auto point = [&](int r, const float4 &tp, const float4 &z1, const float4 &z2, const float4 &z3) {
+            // raw bytes of this frame's 16 points first: their shared-memory latency is paid once, up front
+            uint32_t cur[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
                 const uint32_t a = sm.raw[slot][0][t + NT * r];
                 const uint32_t b = sm.raw[slot][1][t + NT * r];
-                const uint32_t w = __byte_perm(a, b, 0x5410);     // (I0,Q0,I1,Q1)
+                cur[r] = __byte_perm(a, b, 0x5410);               // (I0,Q0,I1,Q1)
+            }
+            auto point = [&](int r, const float4 &tp, const float4 &z1, const float4 &z2, const float4 &z3) {
+                const uint32_t w = cur[r];
                 const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
                 const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
                 v[r] = {f2fmas(yr, tp.x, f2(z1.x, z1.y)), f2fmas(yi, tp.x, f2(z1.z, z1.w))};
