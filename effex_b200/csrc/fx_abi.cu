@@ -53,6 +53,7 @@ struct fx_handle {
     int plan_grid = 0;
     bool parts_per_block = false;              // generic path: one partial per block
 
+    double *d_int_scratch = nullptr;                              // integrate: [64][4N] partial sums
     float2 *d_g0 = nullptr, *d_g1 = nullptr, *d_gtmp = nullptr;   // generic-path frame buffers
     size_t g_cap = 0;                                             // elements per buffer
 
@@ -138,10 +139,9 @@ int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long l
     if (chunks < 1) chunks = 1;
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
         const long long nb = std::min<long long>(65535, n_blocks - b0);
-        dim3 grid((unsigned)chunks, (unsigned)nb);
-        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, h->d_sums + 4 * b0, 4);
-        FX_LAUNCH_CHECK(h, "block_sums");
-        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq1 + 2 * S * b0, S, h->d_sums + 4 * b0 + 2, 4);
+        dim3 grid((unsigned)chunks, (unsigned)nb, 2);
+        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, d_iq1 + 2 * S * b0, S,
+                                                                   h->d_sums + 4 * b0, 4);
         FX_LAUNCH_CHECK(h, "block_sums");
     }
     return FX_OK;
@@ -365,9 +365,14 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     const int N = h->cfg.nbins;
     if (d_acc_x) {
         const int n_segs = h->parts_per_block ? (int)n_blocks : (int)h->h_segs.size();
-        fx::generic::integrate_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(
-            h->d_part_x, h->d_part_a, N, n_segs, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-        FX_LAUNCH_CHECK(h, "integrate");
+        const int G = std::max(1, std::min(64, n_segs / 4));
+        if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)N));
+        fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
+            h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
+        FX_LAUNCH_CHECK(h, "integrate_stage1");
+        fx::generic::integrate_stage2_kernel<<<(4 * N + 255) / 256, 256, 0, h->stream>>>(
+            h->d_int_scratch, N, G, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+        FX_LAUNCH_CHECK(h, "integrate_stage2");
     }
     if (!d_xspec) return FX_OK;
     dim3 grid((N + 255) / 256, 1);
@@ -559,7 +564,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums, h->d_part_x,
-                    h->d_part_a, h->d_plan, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};
@@ -732,7 +737,7 @@ int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames) {
     if (rc) return rc;
     FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4, h->stream));
     long long chunks = std::min<long long>(64, std::max<long long>(1, h->cfg.num_samp / 8192));
-    fx::generic::block_sums_kernel<<<dim3((unsigned)chunks, 1), 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, h->d_sums, 4);
+    fx::generic::block_sums_kernel<<<dim3((unsigned)chunks, 1, 1), 256, 0, h->stream>>>(d_iq, d_iq, h->cfg.num_samp, h->d_sums, 4);
     FX_LAUNCH_CHECK(h, "block_sums");
     dim3 grid((N + 255) / 256, P, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);

@@ -12,12 +12,14 @@ namespace generic {
 // ---------------------------------------------------------------------------
 // Exact per-block byte sums (for the DC removal of effex.py:394-395).
 // sums[b][0] += sum of I bytes, sums[b][1] += sum of Q bytes (stride: sums + b*stride).
-// grid = (chunks, n_blocks).  HBM-bound streaming read.
+// grid = (chunks, n_blocks, channels).  HBM-bound streaming read.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restrict__ iq, long long S,
-                                                         unsigned long long *__restrict__ sums, int stride) {
+__global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restrict__ iq0,
+                                                         const uint8_t *__restrict__ iq1, long long S,
+                                                         unsigned long long *__restrict__ sums0, int stride) {
     const int b = blockIdx.y;
-    const uint8_t *base = iq + 2ll * S * b;
+    const uint8_t *base = (blockIdx.z ? iq1 : iq0) + 2ll * S * b;
+    unsigned long long *sums = sums0 + 2 * blockIdx.z;          // [block][channel][component]
     unsigned int si = 0, sq = 0;
     const long long nbytes = 2ll * S;
     const bool aligned = ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
@@ -233,25 +235,40 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__rest
     if (auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
 }
 
-// integrate: float64 accumulators += sum over all segments of the call (natural order, no rot)
-__global__ void __launch_bounds__(256) integrate_kernel(const float2 *__restrict__ part_x,
-                                                        const float2 *__restrict__ part_a, int N, int n_segs,
-                                                        double frames, double *__restrict__ acc_x,
-                                                        double *__restrict__ acc_a0, double *__restrict__ acc_a1,
-                                                        double *__restrict__ acc_frames) {
+// integrate: float64 accumulators += sum over all segments of the call (natural order, no rot).
+// Two deterministic stages: grid (ceil(N/256), G) partial sums over segment slices into scratch[G][4N],
+// then one pass that folds the G slices into the accumulators.
+__global__ void __launch_bounds__(256) integrate_stage1_kernel(const float2 *__restrict__ part_x,
+                                                               const float2 *__restrict__ part_a, int N, int n_segs,
+                                                               double *__restrict__ scratch) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
+    const int G = gridDim.y, g = blockIdx.y;
+    const int s0 = (int)((long long)n_segs * g / G), s1 = (int)((long long)n_segs * (g + 1) / G);
     double xr = 0, xi = 0, a0 = 0, a1 = 0;
-    for (int s = 0; s < n_segs; ++s) {
+    for (int s = s0; s < s1; ++s) {
         const float2 x = part_x[(long long)s * N + c];
         const float2 a = part_a[(long long)s * N + c];
         xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
     }
-    acc_x[2 * c] += xr;
-    acc_x[2 * c + 1] += xi;
-    acc_a0[c] += a0;
-    acc_a1[c] += a1;
-    if (c == 0 && acc_frames) *acc_frames += frames;
+    double *o = scratch + (long long)g * 4 * N;
+    o[2 * c] = xr;
+    o[2 * c + 1] = xi;
+    o[2 * N + c] = a0;
+    o[3 * N + c] = a1;
+}
+__global__ void __launch_bounds__(256) integrate_stage2_kernel(const double *__restrict__ scratch, int N, int G,
+                                                               double frames, double *__restrict__ acc_x,
+                                                               double *__restrict__ acc_a0, double *__restrict__ acc_a1,
+                                                               double *__restrict__ acc_frames) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // index into the 4N-element slice
+    if (i >= 4 * N) return;
+    double v = 0;
+    for (int g = 0; g < G; ++g) v += scratch[(long long)g * 4 * N + i];
+    if (i < 2 * N) acc_x[i] += v;
+    else if (i < 3 * N) acc_a0[i - 2 * N] += v;
+    else acc_a1[i - 3 * N] += v;
+    if (i == 0 && acc_frames) *acc_frames += frames;
 }
 
 // ---------------------------------------------------------------------------

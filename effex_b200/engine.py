@@ -142,8 +142,12 @@ class FxEngine:
         return (x, a0, a1) if autos else x
 
     def new_accumulators(self):
-        z = lambda n: torch.zeros(n, dtype=torch.float64, device=self.tdev)
-        return {"x": z(2 * self.nbins), "a0": z(self.nbins), "a1": z(self.nbins), "frames": z(1)}
+        """float64 accumulators of one integration: views into ONE flat buffer, so the cross-GPU
+        reduce is a single collective on `acc["flat"]` and clearing is a single memset."""
+        n = self.nbins
+        flat = torch.zeros(4 * n + 1, dtype=torch.float64, device=self.tdev)
+        return {"flat": flat, "x": flat[:2 * n], "a0": flat[2 * n:3 * n], "a1": flat[3 * n:4 * n],
+                "frames": flat[4 * n:]}
 
     def integrate(self, iq0, iq1, acc, n_blocks: int | None = None):
         """fx_integrate: add this call's un-normalised sums into float64 accumulators."""

@@ -36,6 +36,9 @@ def reduce_accumulators(acc: dict, dst: int = 0, group=None) -> dict:
     on dst; other ranks' tensors are left unspecified by the collective)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return acc
+    if "flat" in acc:                       # FxEngine.new_accumulators: already one buffer
+        dist.reduce(acc["flat"], dst=dst, op=dist.ReduceOp.SUM, group=group)
+        return acc
     flat = torch.cat([acc[k].reshape(-1) for k in ACC_KEYS])
     dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
     off = 0
