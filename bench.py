@@ -337,7 +337,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(host_out.nbytes), "steps": e2e_steps,
                     "api": "FxEngine.process_host -> fx_process_host (pinned host buffers)"},
             "gpu_launches": int(launches) * world, "host_issue_ms_per_step": host_issue_ms,
-            "roofline": {"bound": "hbm", "kernel": "fx::fused4096::fused_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "fx::fused4096::fused_kernel_stag", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic_per_launch(), "peak_source": peak_src,
                          "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
