@@ -17,6 +17,7 @@ FX_ERR_CUDA = -2
 FX_ERR_UNSUPPORTED = -3
 FX_ERR_STATE = -4
 FX_FLAG_FORCE_GENERIC = 1
+FX_FLAG_LOCKSTEP_KERNEL = 2
 
 
 class FxConfig(C.Structure):
@@ -45,6 +46,8 @@ SIGNATURES = {
     "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),
     "fx_lag_c64": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "fx_lag_u8": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "fx_csv_rows_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "fx_csv_format_rows": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fx_dev_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
     "fx_dev_free": (C.c_int, [_VP, _VP]),
     "fx_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(_VP)]),

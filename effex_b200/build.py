@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeffex_fx.so")
-SOURCES = ["fx_abi.cu"]
+SOURCES = ["fx_abi.cu", "fx_csv.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     if out is None and not force and not _stale():
         return LIB
     out = out or LIB
-    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-pthread", "-shared",
            "-o", out] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd += ["-Xptxas", "-v"]

@@ -56,12 +56,16 @@ def main(argv=None):
                      extended=args.extended, output_file=args.output)
     S = int(cor.num_samp)
     n_blocks = int(np.ceil(cor.run_time * cor.bandwidth / S))
-    if args.input0 and args.input1:
-        raw0 = np.fromfile(args.input0, dtype=np.uint8, count=2 * S * n_blocks)
-        raw1 = np.fromfile(args.input1, dtype=np.uint8, count=2 * S * n_blocks)
+    if args.input0 and args.input1 and args.mode != 'test':
+        from .correlator import run_files
+        run_files(cor, args.input0, args.input1)          # streamed from disk in chunks of whole blocks
     else:
-        raw0, raw1 = synth.tiled_recording(n_blocks, S, base_blocks=min(8, n_blocks), delay=args.synthetic_delay)
-    cor.run_recording(raw0, raw1)
+        if args.input0 and args.input1:
+            raw0 = np.fromfile(args.input0, dtype=np.uint8, count=2 * S * n_blocks)
+            raw1 = np.fromfile(args.input1, dtype=np.uint8, count=2 * S * n_blocks)
+        else:
+            raw0, raw1 = synth.tiled_recording(n_blocks, S, base_blocks=min(8, n_blocks), delay=args.synthetic_delay)
+        cor.run_recording(raw0, raw1)
     cor.close()
     print(f'wrote {cor.output_file}; estimated delay {1e6 * cor.calibrated_delay:.6f} us')
     if not args.omit_plot:

@@ -272,6 +272,40 @@ class Correlator:
         return out
 
 
+def run_files(cor: "Correlator", path0: str, path1: str, write_csv: bool = True, calibrate: bool = True):
+    """Spectrum/continuum run over two raw recordings on disk, streamed chunk by chunk
+    (`ingest.RecordingReader`) through the host pipeline.  Same row semantics as run_recording."""
+    from .ingest import RecordingReader
+    S = int(cor.num_samp)
+    if cor.mode == 'TEST':
+        raise ValueError("TEST mode sweeps the delay per block; use run_recording")
+    if write_csv:
+        cor._write_metadata()
+    skip = 0
+    if calibrate:
+        head0 = np.fromfile(path0, dtype=np.uint8, count=2 * S)
+        head1 = np.fromfile(path1, dtype=np.uint8, count=2 * S)
+        if head0.size == 2 * S and head1.size == 2 * S:
+            cor.gpu_iq_0 = torch.from_numpy(head0).to(f"cuda:{cor.device}")
+            cor.gpu_iq_1 = torch.from_numpy(head1).to(f"cuda:{cor.device}")
+            cor._calibrate_task()
+            skip = 1
+    reader = RecordingReader(path0, path1, S, batch_blocks=cor.batch_blocks, skip_blocks=skip)
+    eng = cor._main_engine(max_blocks=max(1, min(cor.batch_blocks, reader.n_blocks)))
+    rows = []
+    for raw0, raw1, first, nb in reader:
+        out = eng.process_host(raw0, raw1, nb)
+        if cor.mode == 'CONTINUUM':
+            out = (out.astype(np.complex128).mean(axis=1) / cor.bandwidth).reshape(-1, 1)
+        if write_csv:
+            cor._write_data(out)
+        rows.append(out)
+    if not rows:
+        return np.zeros((0, cor.nbins), dtype=np.complex64)
+    out = np.concatenate(rows, axis=0)
+    return out.reshape(-1) if cor.mode == 'CONTINUUM' else out
+
+
 def _to_numpy(a):
     if isinstance(a, torch.Tensor):
         return a.detach().cpu().numpy()

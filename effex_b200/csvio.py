@@ -27,7 +27,8 @@ def write_metadata(path, run_time, bandwidth, frequency, num_samp, nbins, gain, 
                 np.savetxt(fh, [])
 
 
-def format_rows(rows) -> str:
+def format_rows_py(rows) -> str:
+    """Pure-Python formatter (complex128 precision kept; used for CONTINUUM/TEST scalars)."""
     rows = np.asarray(rows)
     if rows.ndim == 1:
         rows = rows.reshape(1, -1)
@@ -38,8 +39,30 @@ def format_rows(rows) -> str:
     return '\n'.join(out) + '\n'
 
 
+def format_rows(rows, n_threads: int = 0) -> bytes:
+    """complex64 rows -> the bytes np.savetxt would write, through the library's parallel C
+    formatter (fx_csv_format_rows).  Other dtypes fall back to the Python formatter."""
+    rows = np.asarray(rows)
+    if rows.ndim == 1:
+        rows = rows.reshape(1, -1)
+    if rows.dtype != np.complex64:
+        return format_rows_py(rows).encode()
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows)
+    n_rows, nbins = rows.shape
+    cap = lib.fx_csv_rows_bound(n_rows, nbins)
+    buf = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    rc = lib.fx_csv_format_rows(rows.ctypes.data, n_rows, nbins, n_threads, buf, cap, C.byref(n))
+    if rc != 0:
+        raise ValueError(f"fx_csv_format_rows failed ({rc})")
+    return buf.raw[:n.value]
+
+
 def append_rows(path, rows):
-    with open(path, 'a') as fh:
+    with open(path, 'ab') as fh:
         fh.write(format_rows(rows))
 
 

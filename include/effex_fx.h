@@ -138,6 +138,15 @@ int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blo
 int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
               int64_t *imax, float nbhd[3]);
 
+/* ---- CSV rows (host side; replaces np.savetxt in Correlator._write_data, effex.py:687-696) ----
+ * Formats n_rows rows of nbins complex64 values exactly as `np.savetxt(fh, [row], delimiter=',')`
+ * writes them for complex128 (" (%.18e%+.18ej)" per element, ',' between, '\n' after each row),
+ * in parallel over rows.  h_out must hold fx_csv_rows_bound(n_rows, nbins) bytes; *out_len gets the
+ * number of bytes written (no terminating NUL).  n_threads < 1 = all hardware threads.            */
+size_t fx_csv_rows_bound(int64_t n_rows, int64_t nbins);
+int fx_csv_format_rows(const float *h_rows, int64_t n_rows, int64_t nbins, int n_threads,
+                       char *h_out, size_t out_cap, size_t *out_len);
+
 /* ---- memory helpers (so a non-torch host can drive the library) --------- */
 int fx_dev_alloc(fx_handle *h, size_t bytes, void **d_ptr);
 int fx_dev_free(fx_handle *h, void *d_ptr);

@@ -87,6 +87,21 @@ def test_fused_equals_generic_path(c1):
     ef.close(); eg.close()
 
 
+def test_staggered_equals_lockstep_kernel(c1):
+    """The two fused kernels (staggered/TMEM transposed FIR vs lock-step direct FIR) differ only in
+    float32 summation order."""
+    S, N, nb = c1["S"], c1["N"], c1["nb"]
+    d0, d1 = dev(c1["raw0"]), dev(c1["raw1"])
+    es = FxEngine(S, N, 4, max_blocks=nb)
+    el = FxEngine(S, N, 4, max_blocks=nb, lockstep_kernel=True)
+    xs, a0s, a1s = es.process(d0, d1, nb, autos=True)
+    xl, a0l, a1l = el.process(d0, d1, nb, autos=True)
+    for b in range(nb):
+        assert_close(xs[b].cpu().numpy(), xl[b].cpu().numpy(), tol=2e-6, what=f"block {b}")
+        assert_close(a0s[b].cpu().numpy(), a0l[b].cpu().numpy(), tol=2e-6, what=f"auto0 block {b}")
+    es.close(); el.close()
+
+
 @pytest.mark.parametrize("nb", [1, 2, 5, 149, 300])
 def test_fused_segment_plans_agree(c1, nb):
     """Every block count gets its own partition of the frames into per-CTA segments; rows must not
