@@ -52,36 +52,67 @@ __device__ __forceinline__ void radix4(C2 &a0, C2 &a1, C2 &a2, C2 &a3) {
 // register position j of dft16() output holds Y[perm16(j)] (base-4 digit reversal)
 __host__ __device__ constexpr int perm16(int j) { return (j >> 2) + 4 * (j & 3); }
 
-// forward 16-point DFT in place on 16 channel-packed complex registers.
+// ---- helpers with a folded real scale: every one is a pair of FFMA2 ---------------------------
+// (x + c*y, y - c*x) = z * (1 - i*c): a twiddle cos*(1 - i*tan) without its cos factor
+__device__ __forceinline__ C2 ctw(C2 z, float c) { return {f2fmas(z.i, c, z.r), f2fmas(z.r, -c, z.i)}; }
+__device__ __forceinline__ C2 cadd_s(C2 a, float s, C2 b) { return {f2fmas(b.r, s, a.r), f2fmas(b.i, s, a.i)}; }
+// a + (-i)*s*b  and  a + (+i)*s*b
+__device__ __forceinline__ C2 cadd_mi_s(C2 a, float s, C2 b) { return {f2fmas(b.i, s, a.r), f2fmas(b.r, -s, a.i)}; }
+__device__ __forceinline__ C2 cadd_pi_s(C2 a, float s, C2 b) { return {f2fmas(b.i, -s, a.r), f2fmas(b.r, s, a.i)}; }
+
+// second-layer radix-4 whose inputs carry real scales that are folded into the butterfly's FMAs:
+//   a1 = al1*a1p, a2 = al2*a2p, a3 = (ratio*al1)*a3p   ->   (a0..a3) := radix4(a0, a1, a2, a3)
+__device__ __forceinline__ void radix4_scaled(C2 &a0, C2 &a1p, C2 &a2p, C2 &a3p, float al2, float ratio, float al1) {
+    const C2 s02 = cadd_s(a0, al2, a2p), d02 = cadd_s(a0, -al2, a2p);
+    const C2 s13 = cadd_s(a1p, ratio, a3p), d13 = cadd_s(a1p, -ratio, a3p);
+    a0 = cadd_s(s02, al1, s13);
+    a2p = cadd_s(s02, -al1, s13);
+    a1p = cadd_mi_s(d02, al1, d13);
+    a3p = cadd_pi_s(d02, al1, d13);
+}
+
+// forward 16-point DFT in place on 16 channel-packed complex registers (144 packed-FP32 ops).
+// Radix 4 x 4; the inner twiddles W16^m are written as alpha*(1 - i*tan) so that only the cheap
+// (1 - i*tan) part is applied to the data (2 FFMA2, or 2 FADD2 for m = 2, 6, or nothing for m = 4) and
+// the real factor alpha rides for free on the second layer's additions, which become FFMA2.
 __device__ __forceinline__ void dft16(C2 (&v)[16]) {
     constexpr float C1 = 0.92387953251128674f;   // cos(pi/8)
     constexpr float S1 = 0.38268343236508977f;   // sin(pi/8)
     constexpr float R2 = 0.70710678118654752f;   // sqrt(1/2)
+    constexpr float T1 = 0.41421356237309505f;   // tan(pi/8)
+    constexpr float IT1 = 2.41421356237309505f;  // 1/tan(pi/8) = tan(3pi/8)
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) radix4(v[nb], v[nb + 4], v[nb + 8], v[nb + 12]);
-    // internal twiddles W16^(nb*ka) on v[nb + 4*ka]
-    v[5] = cmuls(v[5], C1, -S1);                                   // W^1
-    {   // W^2 = (1-i)/sqrt2 : (x+y, y-x)*R2
-        C2 z = v[6];
-        v[6] = {f2muls(f2add(z.r, z.i), R2), f2muls(f2sub(z.i, z.r), R2)};
-        z = v[9];
-        v[9] = {f2muls(f2add(z.r, z.i), R2), f2muls(f2sub(z.i, z.r), R2)};
+    // ka = 0: no twiddles
+    radix4(v[0], v[1], v[2], v[3]);
+    // ka = 1: W^1 = C1(1 - i T1), W^2 = R2(1 - i), W^3 = S1(1 - i/T1)
+    {
+        C2 a1 = ctw(v[5], T1);
+        C2 a2 = {f2add(v[6].r, v[6].i), f2sub(v[6].i, v[6].r)};
+        C2 a3 = ctw(v[7], IT1);
+        radix4_scaled(v[4], a1, a2, a3, R2, T1, C1);
+        v[5] = a1; v[6] = a2; v[7] = a3;
     }
-    v[7] = cmuls(v[7], S1, -C1);                                   // W^3
-    v[13] = cmuls(v[13], S1, -C1);                                 // W^3
-    {   // W^4 = -i : (y, -x)
-        C2 z = v[10];
-        v[10] = {z.i, f2neg(z.r)};
+    // ka = 2: W^2 = R2(1 - i), W^4 = -i, W^6 = -R2(1 + i)
+    {
+        C2 a1 = {f2add(v[9].r, v[9].i), f2sub(v[9].i, v[9].r)};
+        C2 a2 = {v[10].i, f2neg(v[10].r)};
+        C2 a3 = {f2sub(v[11].r, v[11].i), f2add(v[11].r, v[11].i)};
+        const C2 s02 = cadd(v[8], a2), d02 = csub(v[8], a2);
+        const C2 s13 = csub(a1, a3), d13 = cadd(a1, a3);       // ratio = -1
+        v[8] = cadd_s(s02, R2, s13);
+        v[10] = cadd_s(s02, -R2, s13);
+        v[9] = cadd_mi_s(d02, R2, d13);
+        v[11] = cadd_pi_s(d02, R2, d13);
     }
-    {   // W^6 = (-1-i)/sqrt2 : (y-x, -(x+y))*R2
-        C2 z = v[11];
-        v[11] = {f2muls(f2sub(z.i, z.r), R2), f2muls(f2add(z.r, z.i), -R2)};
-        z = v[14];
-        v[14] = {f2muls(f2sub(z.i, z.r), R2), f2muls(f2add(z.r, z.i), -R2)};
+    // ka = 3: W^3 = S1(1 - i/T1), W^6 = -R2(1 + i), W^9 = -C1(1 - i T1)
+    {
+        C2 a1 = ctw(v[13], IT1);
+        C2 a2 = {f2sub(v[14].r, v[14].i), f2add(v[14].r, v[14].i)};
+        C2 a3 = ctw(v[15], T1);
+        radix4_scaled(v[12], a1, a2, a3, -R2, -IT1, S1);
+        v[13] = a1; v[14] = a2; v[15] = a3;
     }
-    v[15] = cmuls(v[15], -C1, S1);                                 // W^9 = -W^1
-#pragma unroll
-    for (int ka = 0; ka < 4; ++ka) radix4(v[4 * ka], v[4 * ka + 1], v[4 * ka + 2], v[4 * ka + 3]);
 }
 
 // ---- launch bookkeeping ------------------------------------------------------
