@@ -238,12 +238,12 @@ def run_ours(args):
 
     def step():
         if world == 1:
-            eng.process(d0, d1, N_BLOCKS, out=out)
+            eng.process(d0, d1, N_BLOCKS, out=out, inputs_ready=True)    # the recording is resident in HBM
             return
         acc = accs[counter[0] & 1]
         counter[0] += 1
         eng.stream.wait_stream(side)                 # this set's previous reduce + clear have finished
-        eng.process(d0, d1, N_BLOCKS, out=out, acc=acc)
+        eng.process(d0, d1, N_BLOCKS, out=out, acc=acc, inputs_ready=True)
         side.wait_stream(eng.stream)
         with torch.cuda.stream(side):
             # the one collective of the path: reduce the small per-integration accumulators to rank 0
@@ -291,6 +291,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
     value = world * N_BLOCKS * S * args.steps / (max_ms * 1e-3) / 1e6
+
+    # the fused kernel alone (no overlap with the next step's byte-sum pre-pass): a few synchronised launches
+    eng.enable_timing(True)
+    eng.reset_counters()
+    for _ in range(5):
+        eng.process(d0, d1, N_BLOCKS, out=out, inputs_ready=True)
+        eng.sync()
+    iso_ms, iso_n = eng.dominant_kernel_time()
+    eng.enable_timing(False)
+    kernel_ms_isolated = iso_ms / max(iso_n, 1)
 
     if args.profile:
         if rank == 0:
@@ -340,9 +350,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "fx::fused4096::fused_kernel_stag", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic_per_launch(), "peak_source": peak_src,
-                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_ms_isolated": kernel_ms_isolated, "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_BLOCK * N_BLOCKS,
-                         "note": "FP32-pipe bound, not HBM bound: see DESIGN.md (roofline)"},
+                         "note": "FP32-pipe bound, not HBM bound: see DESIGN.md (roofline). kernel_ms_per_launch is event-bracketed inside the timed region and includes queueing behind the overlapped pre-pass of the next step; kernel_ms_isolated is the same kernel launched alone"},
             "clocks": clocks,
         }
         if world == 1:

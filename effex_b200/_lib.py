@@ -60,6 +60,7 @@ SIGNATURES = {
     "fx_enable_timing": (C.c_int, [_VP, C.c_int]),
     "fx_dominant_kernel_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fx_stream": (_VP, [_VP]),
+    "fx_stream_aux": (_VP, [_VP]),
 }
 
 _lib = None

@@ -42,7 +42,12 @@ struct fx_handle {
     bool rot_set = false;
 
     // workspaces
-    unsigned long long *d_sums = nullptr;     // [max_blocks][2][2]
+    unsigned long long *d_sums = nullptr;     // current set: [max_blocks][2][2]
+    unsigned long long *d_sums_set[2] = {nullptr, nullptr};   // double buffered: the byte-sum pre-pass of call k+1
+    cudaStream_t stream_aux = nullptr;        //   runs on its own stream while the fused kernel of call k computes
+    cudaEvent_t ev_sums_ready[2] = {nullptr, nullptr}, ev_sums_free[2] = {nullptr, nullptr};
+    bool sums_free_recorded[2] = {false, false};
+    int sums_idx = 0;
     float2 *d_part_x = nullptr, *d_part_a = nullptr;
     size_t part_cap = 0;                      // in segments
     int *d_plan = nullptr;                     // [segments x4 | cta_first | blk_first]
@@ -133,17 +138,31 @@ int drain_timed(fx_handle *h) {
 // ---- per-block byte sums for both channels --------------------------------
 int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
     const long long S = h->cfg.num_samp;
-    FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, h->stream));
-    long long chunks = S / 16384;          // 4 x 16-byte loads in flight per thread
+    const int set = (h->sums_idx ^= 1);
+    h->d_sums = h->d_sums_set[set];
+    cudaStream_t st = h->stream_aux;
+    // this set was last read by the consumer kernels of two calls ago
+    if (h->sums_free_recorded[set]) FX_CUDA(h, cudaStreamWaitEvent(st, h->ev_sums_free[set], 0));
+    FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, st));
+    long long chunks = S / 8192;            // 128 threads x 4 x 16-byte loads in flight per thread
     if (chunks > 64) chunks = 64;
     if (chunks < 1) chunks = 1;
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
         const long long nb = std::min<long long>(65535, n_blocks - b0);
         dim3 grid((unsigned)chunks, (unsigned)nb, 2);
-        fx::generic::block_sums_kernel<<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, d_iq1 + 2 * S * b0, S,
-                                                                   h->d_sums + 4 * b0, 4);
+        fx::generic::block_sums_kernel<<<grid, 128, 0, st>>>(d_iq0 + 2 * S * b0, d_iq1 + 2 * S * b0, S,
+                                                            h->d_sums + 4 * b0, 4);
         FX_LAUNCH_CHECK(h, "block_sums");
     }
+    FX_CUDA(h, cudaEventRecord(h->ev_sums_ready[set], st));
+    FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_sums_ready[set], 0));
+    return FX_OK;
+}
+// call after the last kernel that reads h->d_sums has been enqueued on h->stream
+int release_sums(fx_handle *h) {
+    const int set = h->sums_idx;
+    FX_CUDA(h, cudaEventRecord(h->ev_sums_free[set], h->stream));
+    h->sums_free_recorded[set] = true;
     return FX_OK;
 }
 
@@ -233,6 +252,8 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long lon
     else
         fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
     FX_LAUNCH_CHECK(h, "fused4096");
+    rc = release_sums(h);
+    if (rc) return rc;
     return end_timed(h, ep);
 }
 
@@ -336,7 +357,7 @@ int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long l
         if (rc) return rc;
     }
     h->parts_per_block = true;
-    return FX_OK;
+    return release_sums(h);
 }
 
 int check_process_args(fx_handle *h, const void *a, const void *b, long long n_blocks) {
@@ -450,6 +471,7 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
                                                                                         h->d_lag_acc);
         FX_LAUNCH_CHECK(h, "lag_accum");
     }
+    if (U8) { rc = release_sums(h); if (rc) return rc; }
     rc = fft_global(h, h->d_lag_acc, h->d_lag_acc_tmp, M, 1, 1);
     if (rc) return rc;
     const int nparts = (int)std::min<long long>(1024, (2 * n + 255) / 256);
@@ -526,7 +548,13 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     CREATE_CUDA(cudaMalloc(&h->d_taps_u8, TN * sizeof(float)));
     CREATE_CUDA(cudaMalloc(&h->d_taps_c, TN * sizeof(float)));
     CREATE_CUDA(cudaMalloc(&h->d_rot, (size_t)cfg->nbins * sizeof(float2)));
-    CREATE_CUDA(cudaMalloc(&h->d_sums, sizeof(unsigned long long) * 4 * (size_t)cfg->max_blocks));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CREATE_CUDA(cudaMalloc(&h->d_sums_set[i], sizeof(unsigned long long) * 4 * (size_t)cfg->max_blocks));
+        CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_sums_ready[i], cudaEventDisableTiming));
+        CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_sums_free[i], cudaEventDisableTiming));
+    }
+    h->d_sums = h->d_sums_set[0];
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      2 * 4096 * (int)sizeof(float2)));
     if (h->fused) {
@@ -562,8 +590,9 @@ int fx_destroy(fx_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
+    if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
-    void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums, h->d_part_x,
+    void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
                     h->d_part_a, h->d_plan, h->d_int_scratch, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
@@ -573,8 +602,13 @@ int fx_destroy(fx_handle *h) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_sums_ready[i]) cudaEventDestroy(h->ev_sums_ready[i]);
+        if (h->ev_sums_free[i]) cudaEventDestroy(h->ev_sums_free[i]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
+    if (h->stream_aux) cudaStreamDestroy(h->stream_aux);
     delete h;
     return FX_OK;
 }
@@ -584,6 +618,7 @@ const char *fx_last_error(const fx_handle *h) { return h ? h->err.c_str() : g_cr
 int fx_sync(fx_handle *h) {
     if (!h) return FX_ERR_INVALID;
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream_aux));
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     FX_CUDA(h, cudaStreamSynchronize(h->stream_copy));
     return FX_OK;
@@ -694,6 +729,7 @@ int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, in
                                    h->stream_copy));
         FX_CUDA(h, cudaEventRecord(h->ev_in[s], h->stream_copy));
         FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+        FX_CUDA(h, cudaStreamWaitEvent(h->stream_aux, h->ev_in[s], 0));
         int rc = process_device(h, h->d_in[s][0], h->d_in[s][1], nb, h->d_out_x[s], h_auto0 ? h->d_out_a0[s] : nullptr,
                                 h_auto1 ? h->d_out_a1[s] : nullptr);
         if (rc) return rc;
@@ -735,15 +771,15 @@ int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames) {
     const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
     int rc = ensure_generic(h, (size_t)P * N);
     if (rc) return rc;
-    FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4, h->stream));
-    long long chunks = std::min<long long>(64, std::max<long long>(1, h->cfg.num_samp / 8192));
-    fx::generic::block_sums_kernel<<<dim3((unsigned)chunks, 1, 1), 256, 0, h->stream>>>(d_iq, d_iq, h->cfg.num_samp, h->d_sums, 4);
-    FX_LAUNCH_CHECK(h, "block_sums");
+    rc = launch_sums(h, d_iq, d_iq, 1);
+    if (rc) return rc;
     dim3 grid((N + 255) / 256, P, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);
     fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, N, T, P, h->d_taps_u8,
                                                                   h->d_sums, 4, h->cfg.dc_remove, out);
     FX_LAUNCH_CHECK(h, "pfb_fir");
+    rc = release_sums(h);
+    if (rc) return rc;
     return fft_batched(h, out, h->d_gtmp, N, P, 0, 1, true);
 }
 
@@ -816,5 +852,6 @@ int fx_dominant_kernel_time(fx_handle *h, double *ms_total, int64_t *launches) {
     return FX_OK;
 }
 void *fx_stream(fx_handle *h) { return h ? (void *)h->stream : nullptr; }
+void *fx_stream_aux(fx_handle *h) { return h ? (void *)h->stream_aux : nullptr; }
 
 }  // extern "C"

@@ -6,6 +6,10 @@
 #pragma once
 #include "fx_common.cuh"
 
+#ifndef FX_SUMS_DP4A
+#define FX_SUMS_DP4A 0
+#endif
+
 namespace fx {
 namespace generic {
 
@@ -14,7 +18,7 @@ namespace generic {
 // sums[b][0] += sum of I bytes, sums[b][1] += sum of Q bytes (stride: sums + b*stride).
 // grid = (chunks, n_blocks, channels).  HBM-bound streaming read.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restrict__ iq0,
+__global__ void __maxnreg__(32) block_sums_kernel(const uint8_t *__restrict__ iq0,
                                                          const uint8_t *__restrict__ iq1, long long S,
                                                          unsigned long long *__restrict__ sums0, int stride) {
     const int b = blockIdx.y;
@@ -27,25 +31,32 @@ __global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restri
     const uint4 *v = reinterpret_cast<const uint4 *>(base);
     const long long step = (long long)gridDim.x * blockDim.x;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+#if FX_SUMS_DP4A
+    auto add4 = [&](uint4 q) {
+        si = __dp4a(q.x, 0x00010001u, si); sq = __dp4a(q.x, 0x01000100u, sq);
+        si = __dp4a(q.y, 0x00010001u, si); sq = __dp4a(q.y, 0x01000100u, sq);
+        si = __dp4a(q.z, 0x00010001u, si); sq = __dp4a(q.z, 0x01000100u, sq);
+        si = __dp4a(q.w, 0x00010001u, si); sq = __dp4a(q.w, 0x01000100u, sq);
+    };
+#else
+    // SIMD-within-a-register on the ALU pipe (LOP3/PRMT/IADD): I bytes and Q bytes of a word are added
+    // as two 16-bit lanes; four words (<= 8 x 255) fit a lane, then the lanes are folded into si / sq
+    auto add4 = [&](uint4 q) {
+        const unsigned e = (q.x & 0x00ff00ffu) + (q.y & 0x00ff00ffu) + (q.z & 0x00ff00ffu) + (q.w & 0x00ff00ffu);
+        const unsigned o = ((q.x >> 8) & 0x00ff00ffu) + ((q.y >> 8) & 0x00ff00ffu) + ((q.z >> 8) & 0x00ff00ffu) +
+                           ((q.w >> 8) & 0x00ff00ffu);
+        si += (e & 0xffffu) + (e >> 16);
+        sq += (o & 0xffffu) + (o >> 16);
+    };
+#endif
     for (; i + 3 * step < nvec; i += 4 * step) {       // 4 independent 16-byte loads in flight
         uint4 q[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) q[u] = __ldg(v + i + u * step);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            si = __dp4a(q[u].x, 0x00010001u, si); sq = __dp4a(q[u].x, 0x01000100u, sq);
-            si = __dp4a(q[u].y, 0x00010001u, si); sq = __dp4a(q[u].y, 0x01000100u, sq);
-            si = __dp4a(q[u].z, 0x00010001u, si); sq = __dp4a(q[u].z, 0x01000100u, sq);
-            si = __dp4a(q[u].w, 0x00010001u, si); sq = __dp4a(q[u].w, 0x01000100u, sq);
-        }
+        for (int u = 0; u < 4; ++u) add4(q[u]);
     }
-    for (; i < nvec; i += step) {
-        const uint4 q = __ldg(v + i);
-        si = __dp4a(q.x, 0x00010001u, si); sq = __dp4a(q.x, 0x01000100u, sq);
-        si = __dp4a(q.y, 0x00010001u, si); sq = __dp4a(q.y, 0x01000100u, sq);
-        si = __dp4a(q.z, 0x00010001u, si); sq = __dp4a(q.z, 0x01000100u, sq);
-        si = __dp4a(q.w, 0x00010001u, si); sq = __dp4a(q.w, 0x01000100u, sq);
-    }
+    for (; i < nvec; i += step) add4(__ldg(v + i));
     // tail (or everything, when the block is not 16-byte aligned): one sample per thread
     for (long long s = nvec * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; s < S;
          s += (long long)gridDim.x * blockDim.x) {
@@ -58,7 +69,7 @@ __global__ void __launch_bounds__(256) block_sums_kernel(const uint8_t *__restri
         wi += __shfl_xor_sync(0xffffffffu, wi, o);
         wq += __shfl_xor_sync(0xffffffffu, wq, o);
     }
-    __shared__ unsigned long long red[2][8];
+    __shared__ unsigned long long red[2][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { red[0][warp] = wi; red[1][warp] = wq; }
     __syncthreads();

@@ -61,6 +61,7 @@ class FxEngine:
         self.frames_per_block = self.num_samp // self.nbins
         self.tdev = torch.device("cuda", self.device)
         self.stream = torch.cuda.ExternalStream(self.lib.fx_stream(self.h), device=self.tdev)
+        self.stream_aux = torch.cuda.ExternalStream(self.lib.fx_stream_aux(self.h), device=self.tdev)
         self.set_window(pfb_window(self.ntaps, self.nbins) if window is None else window)
 
     # ---- lifetime ---------------------------------------------------------
@@ -103,8 +104,15 @@ class FxEngine:
         self.set_rot(rot_vector(self.nbins, bandwidth, frequency, delay))
 
     # ---- stream ordering with torch ----------------------------------------
-    def _enter(self):
-        self.stream.wait_stream(torch.cuda.current_stream(self.tdev))
+    def _enter(self, inputs_ready: bool = False):
+        """Order the engine's streams after the caller's current stream.  `inputs_ready=True`
+        (the caller guarantees the input tensors are complete, e.g. a resident recording) skips it,
+        which lets the byte-sum pre-pass of this call overlap the fused kernel of the previous one."""
+        if inputs_ready:
+            return
+        cur = torch.cuda.current_stream(self.tdev)
+        self.stream.wait_stream(cur)
+        self.stream_aux.wait_stream(cur)      # the byte-sum pre-pass reads the inputs on this stream
 
     def _exit(self):
         torch.cuda.current_stream(self.tdev).wait_stream(self.stream)
@@ -118,7 +126,7 @@ class FxEngine:
 
     # ---- hot path -----------------------------------------------------------
     def process(self, iq0: torch.Tensor, iq1: torch.Tensor, n_blocks: int | None = None, autos: bool = False,
-                out=None, acc=None):
+                out=None, acc=None, inputs_ready: bool = False):
         """fx_process: one fftshifted, rot-applied cross-spectrum row per block.
         With `acc` (see new_accumulators) the same kernel run also adds the
         un-normalised sums into the float64 accumulators (fx_process_acc)."""
@@ -131,7 +139,7 @@ class FxEngine:
             a1 = torch.empty((n_blocks, self.nbins), dtype=torch.float32, device=self.tdev) if autos else None
         else:
             x, a0, a1 = out
-        self._enter()
+        self._enter(inputs_ready)
         pa0 = a0.data_ptr() if a0 is not None else None
         pa1 = a1.data_ptr() if a1 is not None else None
         if acc is None:

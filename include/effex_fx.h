@@ -165,8 +165,12 @@ int64_t fx_kernel_launches(const fx_handle *h);
 int fx_enable_timing(fx_handle *h, int on);
 /* ms spent in, and launches of, the dominant kernel while timing was on. */
 int fx_dominant_kernel_time(fx_handle *h, double *ms_total, int64_t *launches);
-/* raw cudaStream_t of the handle (so a torch host can wait/record on it). */
+/* raw cudaStream_t of the handle (so a torch host can wait/record on it).  The byte-sum
+ * pre-pass (DC means) of every call runs on a second stream, fx_stream_aux, so that it overlaps the
+ * previous call's fused kernel: INPUT buffers must be complete before the call, or be ordered
+ * before BOTH streams; outputs are ordered on fx_stream only.                                       */
 void *fx_stream(fx_handle *h);
+void *fx_stream_aux(fx_handle *h);
 
 #ifdef __cplusplus
 }
