@@ -542,7 +542,11 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         cudaError_t e2_ = (expr);                                                \
         if (e2_ != cudaSuccess) return bail(std::string(#expr) + ": " + cudaGetErrorString(e2_)); \
     } while (0)
-    CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // the main stream outranks the pre-pass stream: queued fused CTAs are placed before byte-sum CTAs
+        int prio_lo = 0, prio_hi = 0;
+        CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CREATE_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+    }
     CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
     const size_t TN = (size_t)cfg->ntaps * cfg->nbins;
     CREATE_CUDA(cudaMalloc(&h->d_taps_u8, TN * sizeof(float)));
