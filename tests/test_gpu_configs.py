@@ -1,0 +1,118 @@
+"""BASELINE.json configs at their full sizes, through the C ABI, against the oracle
+on what the oracle can finish in seconds and through size-independent properties for the rest."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fx_oracle as orc
+from effex_b200 import synth, sharding
+from effex_b200.engine import FxEngine, rot_vector
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def close(got, ref, tol=TOL):
+    got = np.asarray(got, dtype=np.complex128); ref = np.asarray(ref, dtype=np.complex128)
+    return (np.abs(got - ref).max() <= tol * np.abs(ref).max()
+            and np.linalg.norm(got - ref) <= tol * np.linalg.norm(ref))
+
+
+def test_c1_sixty_seconds_of_spectrum_mode():
+    """configs[0]: 550 blocks of S=262144, N=4096.  First and last 3 blocks vs the oracle; all rows
+    finite; the tiled input (period 8 blocks) must give rows that repeat with that period."""
+    S, N, nb = 262144, 4096, 550
+    raw0, raw1 = synth.tiled_recording(nb, S, base_blocks=8, delay=37)
+    tau = 37 / 2.4e6
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    eng.set_delay(2.4e6, 1.4204e9, tau)
+    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    assert np.isfinite(x.view(np.float32)).all()
+    for b in (0, 1, 2, 547, 548, 549):
+        sl = slice(2 * S * b, 2 * S * (b + 1))
+        assert close(x[b], orc.process_block_u8(raw0[sl], raw1[sl], N, 2.4e6, 1.4204e9, tau)), b
+    for b in range(8, nb):
+        assert close(x[b], x[b - 8], 2e-6), b
+    # the calibrated phase is flat: residual phase = -2 pi fc tau (mod 2 pi) across the band
+    ph = np.angle(x[5][N // 4: 3 * N // 4] * np.exp(2j * np.pi * np.mod(1.4204e9 * tau, 1.0)))
+    assert np.abs(ph).mean() < 0.2
+    eng.close()
+
+
+def test_c2_ten_second_lag_search():
+    """configs[1]: cross-spectrum accumulated over 10 s (92 blocks), one inverse FFT, lag = +37 exactly."""
+    S, nb = 262144, 92
+    raw0, raw1 = synth.tiled_recording(nb, S, base_blocks=4, delay=37, seed=99)
+    eng = FxEngine(S, 4096, 4, max_blocks=nb)
+    n, imax, p, q, r = eng.lag(dev(raw0), dev(raw1), nb)
+    assert n - imax == 37
+    assert q > 5 * max(p, r)
+    # 4 distinct blocks accumulated 23 times = 23 x the 4-block accumulation (linearity)
+    n4, imax4, p4, q4, r4 = eng.lag(dev(raw0[:2 * S * 4]), dev(raw1[:2 * S * 4]), 4)
+    assert imax4 == imax
+    assert q == pytest.approx(23 * q4, rel=1e-4)
+    eng.close()
+
+
+def test_c3_high_resolution_line():
+    """configs[2]: resolution 65536, S = 2^24 (extended mode), 4-tap PFB: line at baseband +5752 Hz ->
+    natural bin 157; whole row vs the oracle."""
+    S, N = 2**24, 65536
+    raw0, raw1 = synth.hi_line_pair(S)
+    eng = FxEngine(S, N, 4, max_blocks=1)
+    assert not eng.fused
+    x = eng.process(dev(raw0), dev(raw1), 1).cpu().numpy()[0]
+    ref = orc.process_block_u8(raw0, raw1, N, 2.4e6, 1.4204e9, 0.0)
+    assert close(x, ref)
+    assert int(np.argmax(np.abs(np.fft.ifftshift(x)))) == round(5752.0 / 2.4e6 * N) == 157
+    eng.close()
+
+
+def test_c4_time_sharding_is_invisible():
+    """configs[3] (scaled): a long recording cut into contiguous block ranges (as ranks would take them)
+    gives the same rows and the same integrated spectrum as one pass."""
+    S, N, nb = 262144, 4096, 40
+    raw0, raw1 = synth.tiled_recording(nb, S, base_blocks=5, delay=37, seed=3)
+    d0, d1 = dev(raw0), dev(raw1)
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    acc1 = eng.new_accumulators()
+    rows1 = eng.process(d0, d1, nb, acc=acc1).cpu().numpy()
+    x1, a01, a11 = FxEngine.finish_integration(acc1)
+    for world in (2, 3, 8):
+        acc = eng.new_accumulators()
+        rows = []
+        for rank in range(world):
+            start, count = sharding.shard_range(nb, world, rank)
+            part = eng.new_accumulators()
+            rows.append(eng.process(d0[2 * S * start:2 * S * (start + count)],
+                                    d1[2 * S * start:2 * S * (start + count)], count, acc=part).cpu().numpy())
+            acc["flat"] += part["flat"]               # what the NCCL reduce does
+        rows = np.concatenate(rows)
+        xk, a0k, a1k = FxEngine.finish_integration(acc)
+        for b in range(nb):
+            assert close(rows[b], rows1[b], 2e-6), (world, b)
+        assert close(xk, x1, 1e-6) and close(a0k, a01, 1e-6)      # float32 partials per segment, float64 across
+    eng.close()
+
+
+def test_c5_short_integrations():
+    """configs[4]: bw 3.2e6, resolution 1024, 0.1 s integrations = 312 frames = 319488 samples each;
+    a batch of integrations vs the oracle, and the CSV text of the rows reads back exactly."""
+    S, N, nb = 319488, 1024, 24
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=9, seed=5)
+    tau = 9 / 3.2e6
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    eng.set_delay(3.2e6, 1.4204e9, tau)
+    x = eng.process_host(raw0, raw1, nb)
+    for b in (0, 7, 23):
+        sl = slice(2 * S * b, 2 * S * (b + 1))
+        assert close(x[b], orc.process_block_u8(raw0[sl], raw1[sl], N, 3.2e6, 1.4204e9, tau)), b
+    import io
+    from effex_b200 import csvio
+    back = np.loadtxt(io.BytesIO(csvio.format_rows(x)), dtype=np.complex128, delimiter=',')
+    np.testing.assert_array_equal(back, x.astype(np.complex128))
+    eng.close()
