@@ -1,4 +1,7 @@
-// fx_fused4096.cuh -- fused unpack -> 4-tap PFB FIR -> 4096-point FFT -> X-engine.
+// fx_fused4096.cuh -- fused unpack -> 4-tap PFB FIR -> 4096-point FFT -> X-engine (lock-step version).
+// The production kernel is fused_kernel_stag in fx_fused4096s.cuh; this simpler one (direct-form FIR from
+// three frames of history in registers, taps in shared memory, all warps in the same phase) is kept as an
+// on-device cross-check (FX_FLAG_LOCKSTEP_KERNEL) and shares its helpers, tables and thread mapping.
 //
 // Replaces, for N = 4096, T = 4, the per-block chain of the reference:
 //   pyrtlsdr packed_bytes_to_iq  (uint8 -> complex, effex.py:652)
@@ -97,47 +100,22 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
-// Unpack of byte J of a packed (I0,Q0,I1,Q1) word.  Two exact routes to float(b - 128):
-//  * magic: PRMT the byte into the mantissa of 2^15 (ALU pipe), then one FADD2 per pair of
-//    components subtracts 2^15 + 128 (FMA pipe);
-//  * I2F.S8 Rd, Rs.BJ on the byte biased by 0x80: one instruction, but it issues on the XU
-//    pipe at 16 lanes/clk/SM (measured, profiles/), far too slow to use for all 16 conversions
-//    a point needs per frame.  kI2FTaps of the four taps use it to take work off the FMA pipe.
+// Unpack of byte J of a packed (I0,Q0,I1,Q1) word to the exact float (b - 128): PRMT drops the byte
+// into the mantissa of 2^15 (ALU pipe), then one FADD2 per pair of components subtracts 2^15 + 128
+// (FMA pipe).  (I2F.S8 Rd, Rs.BJ does it in one instruction but issues on the XU pipe at 16
+// lanes/clk/SM -- measured 1.18 ms vs 0.95 ms per launch -- so it is not used.)
 template <int J>
 __device__ __forceinline__ float byte_to_magic(uint32_t w) {
     return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7404u | (J << 4)));
 }
-template <int J>
-__device__ __forceinline__ float sbyte_to_float(uint32_t w) {
-    return (float)(int8_t)(((w ^ 0x80808080u) >> (8 * J)) & 0xffu);
-}
 constexpr float kMagic = 32768.0f + 128.0f;   // 2^15 + 128: f - kMagic = byte - 128, exact
 
 // (I, Q) channel pairs of one packed word as exact floats (b - 128)
-template <bool USE_I2F>
 __device__ __forceinline__ void unpack_pairs(uint32_t w, float2 &pi, float2 &pq) {
-    if (USE_I2F) {
-        pi = f2(sbyte_to_float<0>(w), sbyte_to_float<2>(w));
-        pq = f2(sbyte_to_float<1>(w), sbyte_to_float<3>(w));
-    } else {
-        const float2 mg = f2(-kMagic, -kMagic);
-        pi = f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg);
-        pq = f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg);
-    }
+    const float2 mg = f2(-kMagic, -kMagic);
+    pi = f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg);
+    pq = f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg);
 }
-#ifndef FX_EXP_NOTAPLDS
-#define FX_EXP_NOTAPLDS 0   // experiment: taps from a register instead of smem (WRONG results)
-#endif
-#ifndef FX_EXP_NOTWLDS
-#define FX_EXP_NOTWLDS 0    // experiment: twiddles from registers instead of smem (WRONG results)
-#endif
-#ifndef FX_EXP_NOX
-#define FX_EXP_NOX 0        // experiment: skip the exchange loads/stores (WRONG results)
-#endif
-#ifndef FX_I2F_TAPS
-#define FX_I2F_TAPS 0
-#endif
-constexpr int kI2FTaps = FX_I2F_TAPS;    // how many of the 4 taps unpack through I2F.S8 (XU pipe)
 
 __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
                 const int kmax = fi < T - 1 ? fi : T - 1;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    float4 tp = FX_EXP_NOTAPLDS ? make_float4(nmI.x, nmI.y, nmQ.x, 1e-3f * r) : sm.taps[t + NT * r];
+                    float4 tp = sm.taps[t + NT * r];
                     if (kmax < T - 1) {
                         tp.w = 0.f;
                         if (kmax < 2) tp.z = 0.f;
@@ -246,16 +224,16 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
                     float2 ar = f2muls(nmI, hs);
                     float2 ai = f2muls(nmQ, hs);
                     float2 pi, pq;
-                    unpack_pairs<(kI2FTaps > 0)>(cur[r], pi, pq);
+                    unpack_pairs(cur[r], pi, pq);
                     ar = f2fmas(pi, tp.x, ar);
                     ai = f2fmas(pq, tp.x, ai);
-                    unpack_pairs<(kI2FTaps > 1)>(hist[0][r], pi, pq);
+                    unpack_pairs(hist[0][r], pi, pq);
                     ar = f2fmas(pi, tp.y, ar);
                     ai = f2fmas(pq, tp.y, ai);
-                    unpack_pairs<(kI2FTaps > 2)>(hist[1][r], pi, pq);
+                    unpack_pairs(hist[1][r], pi, pq);
                     ar = f2fmas(pi, tp.z, ar);
                     ai = f2fmas(pq, tp.z, ai);
-                    unpack_pairs<(kI2FTaps > 3)>(hist[2][r], pi, pq);
+                    unpack_pairs(hist[2][r], pi, pq);
                     ar = f2fmas(pi, tp.w, ar);
                     ai = f2fmas(pq, tp.w, ai);
                     v[r] = {ar, ai};
@@ -297,19 +275,20 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             {
                 float2 tw[4], twn[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = FX_EXP_NOTWLDS ? f2(nmI.x, nmQ.y) : sm.twA[4 * b][t];
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twA[4 * b][t];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = FX_EXP_NOTWLDS ? f2(nmI.y, nmQ.x) : sm.twA[g + 1 + 4 * b][t];
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twA[g + 1 + 4 * b][t];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k1 = g + 4 * b;
                         C2 z = v[4 * g + b];
                         if (k1 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        if (!FX_EXP_NOX) { sm.Xr[k1 * NT + t] = z.r; sm.Xi[k1 * NT + t] = z.i; } else v[4 * g + b] = z;
+                        sm.Xr[k1 * NT + t] = z.r;
+                        sm.Xi[k1 * NT + t] = z.i;
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tw[b] = twn[b];
@@ -318,7 +297,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             __syncthreads();
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
-                if (!FX_EXP_NOX) v[n2] = {sm.Xr[k1B * 256 + n2 * 16 + lo], sm.Xi[k1B * 256 + n2 * 16 + lo]};
+                v[n2] = {sm.Xr[k1B * 256 + n2 * 16 + lo], sm.Xi[k1B * 256 + n2 * 16 + lo]};
             }
             // ---- stage B ---------------------------------------------------
             dft16(v);
@@ -328,19 +307,20 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             {
                 float2 tw[4], twn[4];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = FX_EXP_NOTWLDS ? f2(nmI.x, nmQ.y) : sm.twB[4 * b][lo];
+                for (int b = 0; b < 4; ++b) tw[b] = sm.twB[4 * b][lo];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = FX_EXP_NOTWLDS ? f2(nmI.y, nmQ.x) : sm.twB[g + 1 + 4 * b][lo];
+                        for (int b = 0; b < 4; ++b) twn[b] = sm.twB[g + 1 + 4 * b][lo];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k2 = g + 4 * b;
                         C2 z = v[4 * g + b];
                         if (k2 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        if (!FX_EXP_NOX) { sm.Xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r; sm.Xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i; } else v[4 * g + b] = z;
+                        sm.Xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r;
+                        sm.Xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i;
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) tw[b] = twn[b];
@@ -349,7 +329,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
             __syncwarp();
 #pragma unroll
             for (int n3 = 0; n3 < 16; ++n3) {
-                if (!FX_EXP_NOX) v[n3] = {sm.Xr[k1B * 256 + lo * 16 + (n3 ^ lo)], sm.Xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
+                v[n3] = {sm.Xr[k1B * 256 + lo * 16 + (n3 ^ lo)], sm.Xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
             }
             // ---- stage C + X-engine -----------------------------------------
             dft16(v);

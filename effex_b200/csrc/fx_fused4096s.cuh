@@ -29,15 +29,6 @@
 namespace fx {
 namespace fused4096 {
 
-#ifndef FX_STAG_PREFETCH
-#define FX_STAG_PREFETCH 0
-#endif
-#ifndef FX_STAG_DUP
-#define FX_STAG_DUP 0
-#endif
-#ifndef FX_STAG_TAPS
-#define FX_STAG_TAPS 2     // 0: fake taps (timing experiments only, WRONG results), 2: tensor memory
-#endif
 constexpr int RING_S = 2;
 
 struct __align__(16) SmemS {
@@ -82,27 +73,6 @@ __device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b, float4 &c, fl
                  : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "+f"(c.x),
                    "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w)::"memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t (&q)[16], uint32_t taddr) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
-          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-        : "r"(taddr));
-}
-// wait for all outstanding tcgen05.ld; the registers of the load being consumed are routed through
-// the instruction so that no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&q)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
-                   "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15])::"memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, float2 a, float2 b, float2 c, float2 d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-                 "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(b.x)),
-                 "r"(__float_as_uint(b.y)), "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)),
-                 "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y))
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
@@ -119,20 +89,16 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         tma_load_1d(&sm.twA[0][0], prm.twA, (uint32_t)sizeof(sm.twA), &sm.mbar[RING_S]);
         tma_load_1d(&sm.twB[0][0], prm.twB, (uint32_t)sizeof(sm.twB), &sm.mbar[RING_S]);
     }
-#if FX_STAG_TAPS == 2
     // all 512 columns: warps w and w+4 share a lane quarter, 256 columns each =
     // 16 points x [4 taps | z1 | z2 | z3 (4 floats each: re ch0, re ch1, im ch0, im ch1)]
     if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-#endif
     __syncthreads();
-#if FX_STAG_TAPS == 2
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm_pts = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * grp);
 #pragma unroll
     for (int r = 0; r < 16; ++r) tmem_st4(tm_pts + 16 * r, prm.taps[t + NT * r]);
     tmem_wait_st();
-#endif
     bool tables_ready = false;
 
     const int k1B = t >> 4;
@@ -207,7 +173,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             acca[j] = f2(0.f, 0.f);
         }
         C2 v[16];
-#if FX_STAG_TAPS == 2
         // zero FIR state: a segment either starts a block (zero history is the reference's semantics)
         // or first re-ingests the T-1 frames before its first output frame
 #pragma unroll
@@ -216,7 +181,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             tmem_st4(tm_pts + 16 * r + 8, make_float4(0.f, 0.f, 0.f, 0.f));
             tmem_st4(tm_pts + 16 * r + 12, make_float4(0.f, 0.f, 0.f, 0.f));
         }
-#endif
 
         // ---- ingest item j: raw -> history; if `compute`, FIR + stage A -> exchange buffer `buf` ----
         auto fir_stage_a = [&](int j, bool compute, int buf) {
@@ -328,27 +292,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         // step s: FIR/stage A of ingest item s (history-only while s < j0) and stages B, C + X-engine of
         // the frame whose stage A finished in step s-1, in group-dependent order; one CTA barrier per step
         const int j0 = sg.f0 - g0;
-#if FX_STAG_DUP
-        // two copies of the step loop, one per group: no control-flow merges inside a step
-        if (grp == 0) {
-#pragma unroll 1
-            for (int s = 0; s <= n_ing; ++s) {
-                const int q = s - j0 - 1;
-                if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
-                if (q >= 0) fft_rest(q & 1);
-                __syncthreads();
-                if (t == 0 && s < n_ing) refill(s, (ring_cnt + (uint32_t)s) % RING_S);
-            }
-        } else {
-#pragma unroll 1
-            for (int s = 0; s <= n_ing; ++s) {
-                const int q = s - j0 - 1;
-                if (q >= 0) fft_rest(q & 1);
-                if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
-                __syncthreads();
-            }
-        }
-#else
 #pragma unroll 1
         for (int s = 0; s <= n_ing; ++s) {
             const int q = s - j0 - 1;                 // frame (segment-relative) whose exchange buffer is ready
@@ -363,7 +306,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             __syncthreads();
             if (t == 0 && s < n_ing) refill(s, (ring_cnt + (uint32_t)s) % RING_S);
         }
-#endif
         ring_cnt += (uint32_t)n_ing;
 
         // ---- segment epilogue (both exchange buffers are free after the last barrier) ----------------
@@ -389,10 +331,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             __syncthreads();       // the next segment's first exchange stores must not overtake these reads
         }
     }
-#if FX_STAG_TAPS == 2
     __syncthreads();
     if (warp == 0) tmem_dealloc(sm.tmem_base, 512);
-#endif
 }
 
 }  // namespace fused4096
