@@ -246,3 +246,51 @@ def test_errors_are_value_errors():
     with pytest.raises(ValueError):
         eng.process(raw.cpu(), raw.cpu(), 1)   # host tensor on the device entry point
     eng.close()
+
+
+def test_unaligned_inputs_take_the_generic_kernels(c1):
+    """The fused kernel needs 16-byte aligned blocks (TMA bulk copies); a misaligned view must be
+    detected and routed to the generic kernels, with the same answer."""
+    S, N = c1["S"], c1["N"]
+    buf0 = torch.zeros(2 * S + 64, dtype=torch.uint8, device="cuda")
+    buf1 = torch.zeros(2 * S + 64, dtype=torch.uint8, device="cuda")
+    v0, v1 = buf0[2:2 + 2 * S], buf1[6:6 + 2 * S]
+    v0.copy_(torch.from_numpy(c1["raw0"][:2 * S])); v1.copy_(torch.from_numpy(c1["raw1"][:2 * S]))
+    assert v0.data_ptr() % 16 != 0
+    eng = FxEngine(S, N, 4)
+    before = eng.kernel_launches()
+    x = eng.process(v0.contiguous() if not v0.is_contiguous() else v0, v1, 1).cpu().numpy()[0]
+    ref = orc.process_block_u8(c1["raw0"][:2 * S], c1["raw1"][:2 * S], N, 2.4e6, 1.4204e9, 0.0)
+    assert_close(x, ref, what="unaligned input")
+    assert eng.kernel_launches() - before > 4          # FIR x2, FFT x2, X-engine, ... not the 3-launch fused path
+    eng.close()
+
+
+def test_many_small_blocks_and_argument_errors():
+    """More blocks than one grid dimension holds (65535), tiny shapes; zero blocks is an error."""
+    S, N, T, nb = 256, 64, 4, 70000
+    rng = np.random.default_rng(3)
+    base0 = rng.integers(0, 256, size=2 * S * 7, dtype=np.uint8)
+    base1 = rng.integers(0, 256, size=2 * S * 7, dtype=np.uint8)
+    raw0 = np.tile(base0, nb // 7 + 1)[:2 * S * nb]
+    raw1 = np.tile(base1, nb // 7 + 1)[:2 * S * nb]
+    eng = FxEngine(S, N, T, max_blocks=nb)
+    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    ref = orc.process_recording_u8(base0, base1, S, N, 2.4e6, 1.4204e9, 0.0, T, 0, 7)
+    for b in (0, 6, 7, 65534, 65535, 65536, nb - 1):
+        assert_close(x[b], ref[b % 7], what=f"block {b}")
+    with pytest.raises(ValueError):
+        eng.process(dev(raw0), dev(raw1), 0)
+    eng.close()
+
+
+def test_no_dc_removal_generic_and_fused_agree_with_oracle():
+    """dc_remove=0: x = b/127.5 - 1 without the mean subtraction (the unpack of pyrtlsdr alone)."""
+    for S, N in ((2**16, 4096), (2**14, 512)):
+        raw0, raw1 = synth.correlated_pair(S, delay=1, dc0=0.03, dc1=0.02j, seed=8)
+        eng = FxEngine(S, N, 4, dc_remove=False)
+        x = eng.process(dev(raw0), dev(raw1), 1).cpu().numpy()[0]
+        w = orc.pfb_window(4, N)
+        ref = orc.pfb_xcorr(orc.unpack_iq(raw0), orc.unpack_iq(raw1), 4, N, w, 2.4e6, 1.4204e9, 0.0)
+        assert_close(x, ref, what=f"no DC removal N={N}")
+        eng.close()
