@@ -41,6 +41,8 @@ SIGNATURES = {
     "fx_process": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "fx_integrate": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "fx_process_acc": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "fx_span_sums": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_uint64)]),
+    "fx_integrate_stream": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, C.POINTER(C.c_uint64), C.c_int64, _VP, _VP, _VP, _VP]),
     "fx_process_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "fx_pfb_c64": (C.c_int, [_VP, _VP, _VP]),
     "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),

@@ -54,7 +54,7 @@ struct fx_handle {
     size_t segs_cap = 0, off_cta = 0, off_blk = 0;
     std::vector<fx::fused4096::Segment> h_segs;
     std::vector<int> h_cta_first, h_blk_first;
-    long long planned_blocks = -1;
+    long long planned_blocks = -1, planned_P = -1;
     int plan_grid = 0;
     bool parts_per_block = false;              // generic path: one partial per block
 
@@ -136,8 +136,8 @@ int drain_timed(fx_handle *h) {
 }
 
 // ---- per-block byte sums for both channels --------------------------------
-int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
-    const long long S = h->cfg.num_samp;
+int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, long long S = 0) {
+    if (S <= 0) S = h->cfg.num_samp;
     const int set = (h->sums_idx ^= 1);
     h->d_sums = h->d_sums_set[set];
     cudaStream_t st = h->stream_aux;
@@ -145,7 +145,8 @@ int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long l
     if (h->sums_free_recorded[set]) FX_CUDA(h, cudaStreamWaitEvent(st, h->ev_sums_free[set], 0));
     FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, st));
     long long chunks = S / 8192;            // 128 threads x 4 x 16-byte loads in flight per thread
-    if (chunks > 64) chunks = 64;
+    const long long max_chunks = n_blocks >= 64 ? 64 : 4096 / n_blocks;     // few long spans: more CTAs per span
+    if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
         const long long nb = std::min<long long>(65535, n_blocks - b0);
@@ -182,9 +183,10 @@ int ensure_parts(fx_handle *h, size_t n_segs) {
 // Balanced contiguous partition: the n_blocks*P frames of the call are cut into `grid` equal
 // contiguous runs, one per persistent CTA; a run is a list of segments (pieces of blocks).  Only
 // the first segment of a run starts inside a block (and has to re-ingest T-1 frames of history).
-int plan_segments(fx_handle *h, long long n_blocks) {
-    if (h->planned_blocks == n_blocks) return FX_OK;
-    const long long P = h->P, F = n_blocks * P;
+int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
+    if (P <= 0) P = h->P;
+    if (h->planned_blocks == n_blocks && h->planned_P == P) return FX_OK;
+    const long long F = n_blocks * P;
     long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
     h->h_segs.clear();
     h->h_cta_first.assign((size_t)grid + 1, 0);
@@ -227,21 +229,45 @@ int plan_segments(fx_handle *h, long long n_blocks) {
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     FX_CUDA(h, cudaMemcpy(h->d_plan, flat.data(), n_int * sizeof(int), cudaMemcpyHostToDevice));
     h->planned_blocks = n_blocks;
+    h->planned_P = P;
     return ensure_parts(h, h->h_segs.size());
 }
 
-// fused path: sums -> fused kernel -> partial sums [n_blocks*splits][N]
-int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
-    int rc = launch_sums(h, d_iq0, d_iq1, n_blocks);
+// Options of one pass: reference semantics (independent blocks) or one streaming span.
+struct PassOpts {
+    long long units = 0;          // blocks (reference mode) or 1 (streaming span)
+    long long S = 0;              // samples per unit
+    long long P = 0;              // frames per unit
+    const uint8_t *halo0 = nullptr, *halo1 = nullptr;   // streaming: the T-1 frames before the span (raw bytes)
+    const unsigned long long *h_sums = nullptr;         // streaming: recording-wide byte sums (host), or NULL
+    long long mean_count = 0;                            // samples h_sums were taken over
+};
+
+int prepare_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
+    if (!o.h_sums) return launch_sums(h, d_iq0, d_iq1, o.units, o.S);
+    // recording-wide sums supplied by the caller (all-reduced across ranks): just place them
+    const int set = (h->sums_idx ^= 1);
+    h->d_sums = h->d_sums_set[set];
+    if (h->sums_free_recorded[set]) FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_sums_free[set], 0));
+    FX_CUDA(h, cudaMemcpyAsync(h->d_sums, o.h_sums, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));        // h_sums is the caller's stack/array
+    return FX_OK;
+}
+
+// fused path: sums -> fused kernel -> partial sums, one per segment
+int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
+    int rc = prepare_sums(h, d_iq0, d_iq1, o);
     if (rc) return rc;
-    rc = plan_segments(h, n_blocks);
+    rc = plan_segments(h, o.units, o.P);
     if (rc) return rc;
     fx::fused4096::Params prm;
     prm.iq0 = d_iq0; prm.iq1 = d_iq1; prm.sums = h->d_sums;
     prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB;
     prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
     prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
-    prm.S = h->cfg.num_samp; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
+    prm.S = o.S; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
+    prm.mean_count = o.mean_count > 0 ? o.mean_count : o.S;
+    prm.halo0 = o.halo0; prm.halo1 = o.halo1;
     const int grid = h->plan_grid;
     h->parts_per_block = false;
     EventPair ep{};
@@ -314,16 +340,19 @@ int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, i
     return timed ? end_timed(h, ep) : FX_OK;
 }
 
-// generic path for a chunk of blocks: FIR -> FFT -> X-engine into parts[b0 .. b0+nb)
-int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long b0, long long nb) {
-    const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
-    const long long S = h->cfg.num_samp;
+// generic path for a chunk of units: FIR -> FFT -> X-engine into parts[b0 .. b0+nb)
+int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long b0, long long nb,
+                      const PassOpts &o) {
+    const int N = h->cfg.nbins, T = h->cfg.ntaps, P = (int)o.P;
+    const long long S = o.S;
     dim3 grid((N + 255) / 256, P, (unsigned)nb);
     fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
-                                                                  h->d_sums + 4 * b0, 4, h->cfg.dc_remove, h->d_g0);
+                                                                  h->d_sums + 4 * b0, 4, h->cfg.dc_remove, h->d_g0,
+                                                                  b0 == 0 ? o.halo0 : nullptr, o.mean_count);
     FX_LAUNCH_CHECK(h, "pfb_fir");
     fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq1 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
-                                                                  h->d_sums + 4 * b0 + 2, 4, h->cfg.dc_remove, h->d_g1);
+                                                                  h->d_sums + 4 * b0 + 2, 4, h->cfg.dc_remove, h->d_g1,
+                                                                  b0 == 0 ? o.halo1 : nullptr, o.mean_count);
     FX_LAUNCH_CHECK(h, "pfb_fir");
     int rc = fft_batched(h, h->d_g0, h->d_gtmp, N, nb * P, 0, 0, true);
     if (rc) return rc;
@@ -336,24 +365,19 @@ int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, 
     return FX_OK;
 }
 
-long long generic_chunk_blocks(const fx_handle *h) {
-    const size_t per_block = (size_t)h->P * h->cfg.nbins;
-    long long c = (long long)((size_t(1) << 25) / std::max<size_t>(per_block, 1));   // <= 256 MiB per buffer
-    if (c < 1) c = 1;
-    if (c > 16384) c = 16384;
-    return c;
-}
-
-int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
-    int rc = launch_sums(h, d_iq0, d_iq1, n_blocks);
+int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
+    if (o.P > 65535) return fail(h, FX_ERR_UNSUPPORTED, "generic kernels: more than 65535 frames in one unit");
+    int rc = prepare_sums(h, d_iq0, d_iq1, o);
     if (rc) return rc;
-    rc = ensure_parts(h, (size_t)n_blocks);
+    rc = ensure_parts(h, (size_t)o.units);
     if (rc) return rc;
-    const long long chunk = std::min<long long>(generic_chunk_blocks(h), n_blocks);
-    rc = ensure_generic(h, (size_t)chunk * h->P * h->cfg.nbins);
+    const size_t per_unit = (size_t)o.P * h->cfg.nbins;
+    long long chunk = (long long)((size_t(1) << 25) / std::max<size_t>(per_unit, 1));   // <= 256 MiB per buffer
+    chunk = std::max<long long>(1, std::min<long long>(std::min<long long>(chunk, 16384), o.units));
+    rc = ensure_generic(h, (size_t)chunk * per_unit);
     if (rc) return rc;
-    for (long long b0 = 0; b0 < n_blocks; b0 += chunk) {
-        rc = run_generic_chunk(h, d_iq0, d_iq1, b0, std::min(chunk, n_blocks - b0));
+    for (long long b0 = 0; b0 < o.units; b0 += chunk) {
+        rc = run_generic_chunk(h, d_iq0, d_iq1, b0, std::min(chunk, o.units - b0), o);
         if (rc) return rc;
     }
     h->parts_per_block = true;
@@ -373,26 +397,35 @@ bool fused_ok_for(const fx_handle *h, const void *a, const void *b) {
     return h->fused && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
 }
 
-int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks) {
-    if (fused_ok_for(h, d_iq0, d_iq1)) return run_fused(h, d_iq0, d_iq1, n_blocks);
-    return run_generic(h, d_iq0, d_iq1, n_blocks);
+int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
+    const bool halo_ok = ((reinterpret_cast<uintptr_t>(o.halo0) | reinterpret_cast<uintptr_t>(o.halo1)) & 15) == 0;
+    const bool kernel_ok = h->staggered || !o.halo0;      // the lock-step kernel has no halo path
+    if (fused_ok_for(h, d_iq0, d_iq1) && halo_ok && kernel_ok && (o.S % 8) == 0) return run_fused(h, d_iq0, d_iq1, o);
+    return run_generic(h, d_iq0, d_iq1, o);
+}
+
+PassOpts block_opts(const fx_handle *h, long long n_blocks) {
+    PassOpts o;
+    o.units = n_blocks; o.S = h->cfg.num_samp; o.P = h->P;
+    return o;
 }
 
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
                    float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
-                   double *d_acc_a1 = nullptr, double *d_frames = nullptr) {
-    int rc = run_parts(h, d_iq0, d_iq1, n_blocks);
+                   double *d_acc_a1 = nullptr, double *d_frames = nullptr, const PassOpts *span = nullptr) {
+    const PassOpts o = span ? *span : block_opts(h, n_blocks);
+    int rc = run_parts(h, d_iq0, d_iq1, o);
     if (rc) return rc;
     const int N = h->cfg.nbins;
     if (d_acc_x) {
-        const int n_segs = h->parts_per_block ? (int)n_blocks : (int)h->h_segs.size();
+        const int n_segs = h->parts_per_block ? (int)o.units : (int)h->h_segs.size();
         const int G = std::max(1, std::min(64, n_segs / 4));
         if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)N));
         fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
             h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
         FX_LAUNCH_CHECK(h, "integrate_stage1");
         fx::generic::integrate_stage2_kernel<<<(4 * N + 255) / 256, 256, 0, h->stream>>>(
-            h->d_int_scratch, N, G, (double)n_blocks * h->P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+            h->d_int_scratch, N, G, (double)o.units * (double)o.P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
         FX_LAUNCH_CHECK(h, "integrate_stage2");
     }
     if (!d_xspec) return FX_OK;
@@ -690,6 +723,45 @@ int fx_process_acc(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int
     if (!d_acc_x || !d_acc_a0 || !d_acc_a1) return fail(h, FX_ERR_INVALID, "null accumulator pointer");
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
     return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+}
+
+int fx_span_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, uint64_t h_sums[4]) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!h_sums) return fail(h, FX_ERR_INVALID, "null output pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    rc = launch_sums(h, d_iq0, d_iq1, 1, (long long)n_blocks * h->cfg.num_samp);
+    if (rc) return rc;
+    unsigned long long tmp[4];
+    FX_CUDA(h, cudaMemcpyAsync(tmp, h->d_sums, sizeof(tmp), cudaMemcpyDeviceToHost, h->stream));
+    rc = release_sums(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; ++i) h_sums[i] = tmp[i];
+    return FX_OK;
+}
+
+int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                        const uint8_t *d_halo0, const uint8_t *d_halo1, const uint64_t *h_sums, int64_t total_samp,
+                        double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!d_acc_x || !d_acc_a0 || !d_acc_a1) return fail(h, FX_ERR_INVALID, "null accumulator pointer");
+    if ((d_halo0 == nullptr) != (d_halo1 == nullptr)) return fail(h, FX_ERR_INVALID, "give both halos or none");
+    if (h_sums && total_samp < 1) return fail(h, FX_ERR_INVALID, "total_samp must accompany h_sums");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    PassOpts o;
+    o.units = 1;
+    o.S = (long long)n_blocks * h->cfg.num_samp;
+    o.P = o.S / h->cfg.nbins;
+    o.halo0 = d_halo0; o.halo1 = d_halo1;
+    unsigned long long sums_copy[4];
+    if (h_sums) {
+        for (int i = 0; i < 4; ++i) sums_copy[i] = h_sums[i];
+        o.h_sums = sums_copy;
+        o.mean_count = total_samp;
+    }
+    return process_device(h, d_iq0, d_iq1, 1, nullptr, nullptr, nullptr, d_acc_x, d_acc_a0, d_acc_a1, d_frames, &o);
 }
 
 int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,

@@ -63,6 +63,8 @@ struct Params {
     float2 *part_x;                     // [n_segs][N] sum F0*conj(F1) (natural bin order)
     float2 *part_a;                     // [n_segs][N] (sum|F0|^2, sum|F1|^2)
     long long S;                        // samples per block
+    long long mean_count;               // samples the byte sums were taken over (= S unless recording-wide sums are supplied)
+    const uint8_t *halo0, *halo1;       // streaming mode: the (T-1) frames that precede frame 0 of block 0, or NULL
     int n_segs;
     int dc_remove;
 };
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(const Params prm) {
         float2 nmI, nmQ;
         if (prm.dc_remove) {
             const unsigned long long *su = prm.sums + 4ll * sg.block;
-            const double inv = 1.0 / (double)prm.S;
+            const double inv = 1.0 / (double)prm.mean_count;
             nmI = f2((float)(128.0 - (double)su[0] * inv), (float)(128.0 - (double)su[2] * inv));
             nmQ = f2((float)(128.0 - (double)su[1] * inv), (float)(128.0 - (double)su[3] * inv));
         } else {

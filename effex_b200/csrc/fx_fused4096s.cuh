@@ -40,8 +40,8 @@ struct __align__(16) SmemS {
     unsigned long long mbar[RING_S + 1];
     uint32_t tmem_base;
     // TMA producer state of the current segment (written and read by thread 0 only; kept out of registers)
-    const uint8_t *src0, *src1, *nsrc0, *nsrc1;
-    int n_ing, n_ing_next;
+    const uint8_t *src0, *src1, *nsrc0, *nsrc1, *hsrc0, *hsrc1;
+    int n_ing, n_ing_next, n_halo;
 };
 
 // ---- tensor memory helpers (tcgen05; 32 lanes x 32-bit columns per warp quarter) -------------
@@ -114,14 +114,17 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         float2 nmI, nmQ;
         if (prm.dc_remove) {
             const unsigned long long *su = prm.sums + 4ll * sg.block;
-            const double inv = 1.0 / (double)prm.S;
+            const double inv = 1.0 / (double)prm.mean_count;
             nmI = f2((float)(128.0 - (double)su[0] * inv), (float)(128.0 - (double)su[2] * inv));
             nmQ = f2((float)(128.0 - (double)su[1] * inv), (float)(128.0 - (double)su[3] * inv));
         } else {
             nmI = f2(0.5f, 0.5f);
             nmQ = f2(0.5f, 0.5f);
         }
-        const int g0 = sg.f0 - (T - 1) > 0 ? sg.f0 - (T - 1) : 0;
+        // first ingested frame: T-1 frames before the first output frame; before frame 0 of block 0 only
+        // when the caller supplied the preceding samples (streaming mode), otherwise zero history
+        const bool use_halo = prm.halo0 != nullptr && sg.block == 0 && sg.f0 < T - 1;
+        const int g0 = (use_halo || sg.f0 - (T - 1) > 0) ? sg.f0 - (T - 1) : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
         if (t == 0) {
             // the segment after this one (same CTA): its first frames are prefetched during our last ones
@@ -130,8 +133,11 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             Segment ng = sg;
             if (have_next) ng = prm.segs[nseg];
             const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
-            sm.src0 = b0 + (long long)g0 * FRAME_BYTES;
+            sm.src0 = b0 + (long long)g0 * FRAME_BYTES;        // ingest item j reads src + j*FRAME_BYTES ...
             sm.src1 = b1 + (long long)g0 * FRAME_BYTES;
+            sm.n_halo = g0 < 0 ? -g0 : 0;                      // ... except the first n_halo items: halo frames
+            sm.hsrc0 = prm.halo0 + (long long)(T - 1 + g0) * FRAME_BYTES;
+            sm.hsrc1 = prm.halo1 + (long long)(T - 1 + g0) * FRAME_BYTES;
             sm.nsrc0 = prm.iq0 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
             sm.nsrc1 = prm.iq1 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
             sm.n_ing = n_ing;
@@ -140,8 +146,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             for (int j = already; j < pre; ++j) {
                 const uint32_t s = (ring_cnt + j) % RING_S;
                 mbar_expect_tx(&sm.mbar[s], 2 * FRAME_BYTES);
-                tma_load_1d(&sm.raw[s][0][0], sm.src0 + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
-                tma_load_1d(&sm.raw[s][1][0], sm.src1 + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                const bool hal = j < sm.n_halo;
+                tma_load_1d(&sm.raw[s][0][0], (hal ? sm.hsrc0 : sm.src0) + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][1][0], (hal ? sm.hsrc1 : sm.src1) + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
             }
             already = 0;
         }
@@ -152,8 +159,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             const int ni = sm.n_ing;
             const uint8_t *s0 = nullptr, *s1 = nullptr;
             if (jn < ni) {
-                s0 = sm.src0 + (long long)jn * FRAME_BYTES;
-                s1 = sm.src1 + (long long)jn * FRAME_BYTES;
+                const bool hal = jn < sm.n_halo;
+                s0 = (hal ? sm.hsrc0 : sm.src0) + (long long)jn * FRAME_BYTES;
+                s1 = (hal ? sm.hsrc1 : sm.src1) + (long long)jn * FRAME_BYTES;
             } else if (jn - ni < sm.n_ing_next) {
                 s0 = sm.nsrc0 + (long long)(jn - ni) * FRAME_BYTES;
                 s1 = sm.nsrc1 + (long long)(jn - ni) * FRAME_BYTES;

@@ -90,30 +90,35 @@ template <bool U8>
 __global__ void __launch_bounds__(256) pfb_fir_kernel(const void *__restrict__ in, long long S, int N, int T, int P,
                                                       const float *__restrict__ taps,
                                                       const unsigned long long *__restrict__ sums, int sum_stride,
-                                                      int dc_remove, float2 *__restrict__ w) {
+                                                      int dc_remove, float2 *__restrict__ w,
+                                                      const void *__restrict__ halo = nullptr, long long mean_count = 0) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y, b = blockIdx.z;
     if (p >= N) return;
     float mi = 0.f, mq = 0.f;
     if (U8) {
         if (dc_remove) {
-            mi = (float)((double)sums[(long long)b * sum_stride] / (double)S);
-            mq = (float)((double)sums[(long long)b * sum_stride + 1] / (double)S);
+            const double den = (double)(mean_count > 0 ? mean_count : S);
+            mi = (float)((double)sums[(long long)b * sum_stride] / den);
+            mq = (float)((double)sums[(long long)b * sum_stride + 1] / den);
         } else {
             mi = mq = 127.5f;
         }
     }
     float ar = 0.f, ai = 0.f;
-    const int kmax = i < T - 1 ? i : T - 1;
+    // zero history before frame 0 -- unless the caller supplied the T-1 preceding frames (streaming mode)
+    const int kmax = (i < T - 1 && !(halo && b == 0)) ? i : T - 1;
     for (int k = 0; k <= kmax; ++k) {
-        const long long s = (long long)b * S + (long long)(i - k) * N + p;
+        long long s = (long long)b * S + (long long)(i - k) * N + p;
+        const void *src = in;
+        if (i - k < 0) { src = halo; s = (long long)(i - k + T - 1) * N + p; }
         float xr, xi;
         if (U8) {
-            const uchar2 q = reinterpret_cast<const uchar2 *>(in)[s];
+            const uchar2 q = reinterpret_cast<const uchar2 *>(src)[s];
             xr = (float)q.x - mi;
             xi = (float)q.y - mq;
         } else {
-            const float2 q = reinterpret_cast<const float2 *>(in)[s];
+            const float2 q = reinterpret_cast<const float2 *>(src)[s];
             xr = q.x;
             xi = q.y;
         }

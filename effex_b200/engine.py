@@ -171,6 +171,41 @@ class FxEngine:
         self._exit()
         return acc
 
+    def span_sums(self, iq0, iq1, n_blocks: int | None = None) -> np.ndarray:
+        """fx_span_sums: exact byte sums {I0, Q0, I1, Q1} of the span (uint64[4])."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        out = (C.c_uint64 * 4)()
+        self._enter()
+        self._check(self.lib.fx_span_sums(self.h, p0, p1, n_blocks, out), "fx_span_sums")
+        return np.array(list(out), dtype=np.uint64)
+
+    def integrate_stream(self, iq0, iq1, acc, n_blocks: int | None = None, halo0=None, halo1=None, sums=None,
+                         total_samp: int | None = None):
+        """fx_integrate_stream: the span is a piece of one long recording (PFB history carried, `halo`
+        = the (ntaps-1)*nbins samples before it as raw bytes, `sums`/`total_samp` = recording-wide byte sums)."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        hb = 2 * (self.ntaps - 1) * self.nbins
+        ph0 = ph1 = None
+        if halo0 is not None:
+            for t in (halo0, halo1):
+                if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.numel() != hb:
+                    raise ValueError(f"halo must be a contiguous uint8 CUDA tensor of {hb} bytes")
+            ph0, ph1 = halo0.data_ptr(), halo1.data_ptr()
+        csums = None
+        if sums is not None:
+            csums = (C.c_uint64 * 4)(*[int(v) for v in sums])
+        self._enter()
+        rc = self.lib.fx_integrate_stream(self.h, p0, p1, n_blocks, ph0, ph1, csums,
+                                          int(total_samp) if total_samp else 0, acc["x"].data_ptr(),
+                                          acc["a0"].data_ptr(), acc["a1"].data_ptr(), acc["frames"].data_ptr())
+        self._check(rc, "fx_integrate_stream")
+        self._exit()
+        return acc
+
     @staticmethod
     def finish_integration(acc, rot=None):
         """Host epilogue of an integration (after any cross-GPU reduce):

@@ -102,3 +102,31 @@ def engine_compute(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor):
         rows = engine.process(d_iq0[lo:hi], d_iq1[lo:hi], count, acc=acc)
         return rows, acc
     return compute
+
+
+def stream_integrate(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor, group=None, dst: int = 0):
+    """Streaming-history integration of a recording that is time-sharded over the ranks of `group`
+    (rank r holds the r-th contiguous slice, a whole number of blocks, in d_iq0/d_iq1).
+    Exchanges: (1) all-reduce of the 4 byte sums -> recording-wide DC mean; (2) the PFB halo, i.e. the
+    last (ntaps-1)*nbins samples of the left neighbour's slice (all-gather of the tiny tails);
+    (3) one reduce of the float64 accumulators.  Returns the reduced accumulators (valid on dst)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_blocks = d_iq0.numel() // (2 * engine.num_samp)
+    sums = torch.from_numpy(engine.span_sums(d_iq0, d_iq1, n_blocks).astype(np.int64)).to(d_iq0.device)
+    count = torch.tensor([n_blocks * engine.num_samp], dtype=torch.int64, device=d_iq0.device)
+    halo0 = halo1 = None
+    if world > 1:
+        both = torch.cat([sums, count])
+        dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+        sums, count = both[:4], both[4:]
+        hb = 2 * (engine.ntaps - 1) * engine.nbins
+        tails = torch.stack([d_iq0[-hb:], d_iq1[-hb:]]).contiguous()
+        gathered = [torch.empty_like(tails) for _ in range(world)]
+        dist.all_gather(gathered, tails, group=group)
+        if rank > 0:
+            halo0, halo1 = gathered[rank - 1][0].contiguous(), gathered[rank - 1][1].contiguous()
+    acc = engine.new_accumulators()
+    engine.integrate_stream(d_iq0, d_iq1, acc, n_blocks, halo0, halo1, sums.cpu().numpy().astype(np.uint64),
+                            int(count.item()))
+    return reduce_accumulators(acc, dst=dst, group=group)

@@ -108,6 +108,20 @@ int fx_process_acc(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int
                    float *d_xspec, float *d_auto0, float *d_auto1,
                    double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
 
+/* ---- streaming-history variant (north_star: time shards with PFB halos) ---------------------------
+ * The reference restarts the PFB with zero history at every block; the streaming variant
+ * treats the n_blocks blocks of the call as ONE contiguous span of a longer recording: PFB history carries
+ * across the block boundaries, d_halo0/1 hold the raw bytes of the (ntaps-1)*nbins complex samples that
+ * precede the span (NULL = start of the recording: zero history), and the DC mean is h_sums/total_samp when
+ * h_sums != NULL (recording-wide byte sums {I0,Q0,I1,Q1}, e.g. all-reduced over ranks), else the span's own.
+ * It equals the reference's arithmetic applied to the whole recording as one giant block.  Adds the
+ * un-normalised sums of the span's frames into the float64 accumulators like fx_integrate.
+ * fx_span_sums returns the exact byte sums of the span (synchronous).                                  */
+int fx_span_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, uint64_t h_sums[4]);
+int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                        const uint8_t *d_halo0, const uint8_t *d_halo1, const uint64_t *h_sums, int64_t total_samp,
+                        double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
+
 /* fx_process_host: fx_process with HOST buffers (pinned or pageable): H2D of
  * the raw bytes, compute, D2H of the rows, pipelined in chunks on two
  * streams.  Synchronous.  This is the call the reference-facing wrapper

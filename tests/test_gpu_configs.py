@@ -116,3 +116,47 @@ def test_c5_short_integrations():
     back = np.loadtxt(io.BytesIO(csvio.format_rows(x)), dtype=np.complex128, delimiter=',')
     np.testing.assert_array_equal(back, x.astype(np.complex128))
     eng.close()
+
+
+@pytest.mark.parametrize("S,N", [(2**16, 4096), (2**13, 1024)])
+def test_streaming_history_equals_one_giant_block(S, N):
+    """Streaming mode (PFB history carried across blocks, recording-wide mean) = the reference's
+    arithmetic applied to the whole recording as ONE block; and cutting the recording into time shards
+    with halos and global byte sums (what ranks do) changes nothing."""
+    nb = 12
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=7, dc0=0.02 + 0.01j, dc1=-0.015j, seed=17)
+    d0, d1 = dev(raw0), dev(raw1)
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    w = orc.pfb_window(4, N)
+    x0, x1 = orc.block_from_u8(raw0), orc.block_from_u8(raw1)          # ONE block: global mean
+    f0, f1 = orc.spectrometer_poly(x0, 4, N, w), orc.spectrometer_poly(x1, 4, N, w)
+    ref = np.fft.fftshift((f0 * np.conj(f1)).mean(axis=0))
+    ref_a0 = np.fft.fftshift((abs(f0) ** 2).mean(axis=0))
+    acc = eng.new_accumulators()
+    eng.integrate_stream(d0, d1, acc, nb)
+    x, a0, a1 = FxEngine.finish_integration(acc)
+    assert acc["frames"].item() == nb * S // N
+    assert close(x, ref) and close(a0, ref_a0)
+    # reference mode differs (zero history + per-block mean at every block): the two semantics are distinct
+    acc_ref = eng.new_accumulators()
+    eng.integrate(d0, d1, acc_ref, nb)
+    xr, _, _ = FxEngine.finish_integration(acc_ref)
+    assert not close(xr, ref, 1e-3)
+    # time shards with halos
+    sums = eng.span_sums(d0, d1, nb)
+    np.testing.assert_array_equal(sums, [raw0[0::2].sum(dtype=np.uint64), raw0[1::2].sum(dtype=np.uint64),
+                                         raw1[0::2].sum(dtype=np.uint64), raw1[1::2].sum(dtype=np.uint64)])
+    hb = 2 * 3 * N
+    for world in (2, 3, 4):
+        tot = eng.new_accumulators()
+        for rank in range(world):
+            start, count = sharding.shard_range(nb, world, rank)
+            lo, hi = 2 * S * start, 2 * S * (start + count)
+            h0 = d0[lo - hb:lo].contiguous() if rank else None
+            h1 = d1[lo - hb:lo].contiguous() if rank else None
+            part = eng.new_accumulators()
+            eng.integrate_stream(d0[lo:hi], d1[lo:hi], part, count, h0, h1, sums, nb * S)
+            tot["flat"] += part["flat"]
+        xs, a0s, _ = FxEngine.finish_integration(tot)
+        assert close(xs, ref) and close(xs, x, 2e-6) and close(a0s, a0, 2e-6), world
+    eng.close()

@@ -79,3 +79,64 @@ def test_sharded_run_matches_single_process(tmp_path, world):
     np.testing.assert_allclose(got["a1"], a11, rtol=1e-12)
     ref = orc.process_recording_u8(raw0, raw1, S, N, BW, FC, 0.0, T, 0, NB)
     np.testing.assert_allclose(got["x"], ref.mean(axis=0), rtol=1e-10, atol=1e-16)
+
+
+# ---- streaming-history sharding (halo + global byte sums + one reduce) with an oracle-backed engine ----
+class _OracleEngine:
+    """Stands in for FxEngine on CPU: same methods stream_integrate() uses, float64 oracle inside."""
+    num_samp, nbins, ntaps = S, N, T
+
+    def span_sums(self, a, b, nb):
+        a, b = a.numpy(), b.numpy()
+        return np.array([a[0::2].sum(dtype=np.uint64), a[1::2].sum(dtype=np.uint64),
+                         b[0::2].sum(dtype=np.uint64), b[1::2].sum(dtype=np.uint64)], dtype=np.uint64)
+
+    def new_accumulators(self):
+        flat = torch.zeros(4 * N + 1, dtype=torch.float64)
+        return {"flat": flat, "x": flat[:2 * N], "a0": flat[2 * N:3 * N], "a1": flat[3 * N:4 * N], "frames": flat[4 * N:]}
+
+    def integrate_stream(self, a, b, acc, nb, halo0, halo1, sums, total):
+        w = orc.pfb_window(T, N)
+        hist = (T - 1) if halo0 is not None else 0
+
+        def chan(raw, halo, si, sq):
+            raw = np.concatenate([halo.numpy(), raw.numpy()]) if halo is not None else raw.numpy()
+            x = (raw[0::2].astype(np.float64) - float(si) / total) / 127.5 \
+                + 1j * (raw[1::2].astype(np.float64) - float(sq) / total) / 127.5
+            return orc.spectrometer_poly(x, T, N, w)[hist:]          # frames of the halo itself are not output
+        f0 = chan(a, halo0, sums[0], sums[1])
+        f1 = chan(b, halo1, sums[2], sums[3])
+        acc["x"] += torch.from_numpy((f0 * np.conj(f1)).sum(axis=0).view(np.float64).copy())
+        acc["a0"] += torch.from_numpy((abs(f0) ** 2).sum(axis=0))
+        acc["a1"] += torch.from_numpy((abs(f1) ** 2).sum(axis=0))
+        acc["frames"] += f0.shape[0]
+        return acc
+
+
+def _stream_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    raw0, raw1 = synth.correlated_pair(NB * S, delay=3, dc0=0.03, dc1=-0.02j, seed=9)
+    start, count = sharding.shard_range(NB, world, rank)
+    sl = slice(2 * S * start, 2 * S * (start + count))
+    acc = sharding.stream_integrate(_OracleEngine(), torch.from_numpy(raw0[sl].copy()), torch.from_numpy(raw1[sl].copy()))
+    if rank == 0:
+        x, a0, a1 = sharding.finish_integration(acc)
+        np.savez(out, x=x, a0=a0, frames=acc["frames"].numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stream_integrate_across_ranks_equals_one_giant_block(tmp_path):
+    out = str(tmp_path / "s.npz")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_stream_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    raw0, raw1 = synth.correlated_pair(NB * S, delay=3, dc0=0.03, dc1=-0.02j, seed=9)
+    w = orc.pfb_window(T, N)
+    f0 = orc.spectrometer_poly(orc.block_from_u8(raw0), T, N, w)       # the recording as ONE block
+    f1 = orc.spectrometer_poly(orc.block_from_u8(raw1), T, N, w)
+    assert got["frames"][0] == f0.shape[0]
+    np.testing.assert_allclose(got["x"], np.fft.fftshift((f0 * np.conj(f1)).mean(axis=0)), rtol=1e-9, atol=1e-16)
+    np.testing.assert_allclose(got["a0"], np.fft.fftshift((abs(f0) ** 2).mean(axis=0)), rtol=1e-9)
