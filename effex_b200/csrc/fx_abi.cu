@@ -38,6 +38,7 @@ struct fx_handle {
     float *d_taps_c = nullptr;    // [T][N] reversed, unscaled (complex64 input)
     float4 *d_taps4 = nullptr;    // fused layout [N] (k = 0..3)
     float2 *d_twA = nullptr, *d_twB = nullptr;
+    float4 *d_twAp = nullptr, *d_twBp = nullptr;
     float2 *d_rot = nullptr;
     bool rot_set = false;
 
@@ -262,7 +263,7 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     if (rc) return rc;
     fx::fused4096::Params prm;
     prm.iq0 = d_iq0; prm.iq1 = d_iq1; prm.sums = h->d_sums;
-    prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB;
+    prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
     prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
     prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
     prm.S = o.S; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
@@ -611,6 +612,24 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
             }
         CREATE_CUDA(cudaMemcpy(h->d_twA, twA.data(), twA.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaMemcpy(h->d_twB, twB.data(), twB.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        // paired copies: row 2g+h holds (tw[k], tw[k+4]) for k = g + 8h, so one 128-bit load feeds two twiddles
+        std::vector<float4> twAp(8 * 256), twBp(8 * 16);
+        for (int g = 0; g < 4; ++g)
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k = g + 8 * hh;
+                for (int t = 0; t < 256; ++t) {
+                    const float2 a = twA[k * 256 + t], b = twA[(k + 4) * 256 + t];
+                    twAp[(2 * g + hh) * 256 + t] = make_float4(a.x, a.y, b.x, b.y);
+                }
+                for (int n3 = 0; n3 < 16; ++n3) {
+                    const float2 a = twB[k * 16 + n3], b = twB[(k + 4) * 16 + n3];
+                    twBp[(2 * g + hh) * 16 + n3] = make_float4(a.x, a.y, b.x, b.y);
+                }
+            }
+        CREATE_CUDA(cudaMalloc(&h->d_twAp, twAp.size() * sizeof(float4)));
+        CREATE_CUDA(cudaMalloc(&h->d_twBp, twBp.size() * sizeof(float4)));
+        CREATE_CUDA(cudaMemcpy(h->d_twAp, twAp.data(), twAp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(h->d_twBp, twBp.data(), twBp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::fused4096::Smem)));
         CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel_stag, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -629,7 +648,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
-    void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
+    void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
                     h->d_part_a, h->d_plan, h->d_int_scratch, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],

@@ -58,6 +58,7 @@ struct Params {
     const float4 *taps;                 // [N]
     const float2 *twA;                  // [16][256]
     const float2 *twB;                  // [16][16]
+    const float4 *twAp, *twBp;          // the same tables, rows paired (k, k+4) per float4 (staggered kernel)
     const Segment *segs;                // all segments, in global frame order
     const int *cta_first;               // [gridDim.x + 1]: CTA c walks segs[cta_first[c] .. cta_first[c+1])
     float2 *part_x;                     // [n_segs][N] sum F0*conj(F1) (natural bin order)

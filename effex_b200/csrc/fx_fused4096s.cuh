@@ -19,8 +19,8 @@
 //     out_i = t0*y_i + z1 ;  z1' = t1*y_i + z2 ;  z2' = t2*y_i + z3 ;  z3' = t3*y_i
 // (identical arithmetic to the direct form up to float32 summation order; zero state at a block
 // start IS channelize_poly's zero history).  The state z1..z3 (12 floats per point, 48 KB/warp pair)
-// is thread-private, so it lives in tensor memory next to the taps: one tcgen05.ld.x16 and one
-// tcgen05.st.x8 + .x4 per point per frame (measured tcgen05.ld 2.6 KB/clk/SM, tcgen05.st
+// is thread-private, so it lives in tensor memory next to the taps: two tcgen05.ld.x8 and three
+// tcgen05.st.x4 per point per frame, the loads issued one point ahead (measured tcgen05.ld 2.6 KB/clk/SM, tcgen05.st
 // 285 B/clk/SM, tools/ubench_tmem.cu).  Compared with re-unpacking the three history frames this
 // removes 12 of 16 PRMT and 4 of 8 FADD2 per point and the 48 history registers.
 #pragma once
@@ -30,12 +30,18 @@ namespace fx {
 namespace fused4096 {
 
 constexpr int RING_S = 2;
+// exchange planes: 16 tiles of 16 rows x 16 columns, rows padded to 17 elements.  Column-wise and
+// row-wise accesses of a half-warp are both bank-conflict free, and every offset other than the
+// thread's own (row or column) is a compile-time immediate -- no swizzle arithmetic per access.
+constexpr int ROWP = 17;
+constexpr int TILE = 16 * ROWP;
+constexpr int NP = 16 * TILE;
 
 struct __align__(16) SmemS {
-    float2 Xr[2][N];             // 2 x 32 KB exchange planes (re ch0, re ch1), double buffered
-    float2 Xi[2][N];             // 2 x 32 KB exchange planes (im ch0, im ch1)
-    float2 twA[16][NT];          // W4096^(t*k1)
-    float2 twB[16][16];          // W256^(n3*k2)
+    float2 Xr[2][NP];            // 2 x 34 KB exchange planes (re ch0, re ch1), double buffered
+    float2 Xi[2][NP];            // 2 x 34 KB exchange planes (im ch0, im ch1)
+    float4 twA[8][NT];           // row 2g+h: (W4096^(t*k1), W4096^(t*(k1+4))) for k1 = g + 8h  (one LDS.128 per pair)
+    float4 twB[8][16];           // row 2g+h: (W256^(n3*k2), W256^(n3*(k2+4))) for k2 = g + 8h
     unsigned short raw[RING_S][2][N];
     unsigned long long mbar[RING_S + 1];
     uint32_t tmem_base;
@@ -60,12 +66,19 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v) {
                  "r"(__float_as_uint(v.w))
                  : "memory");
 }
-__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
-    uint32_t a, b, c, d;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float4 &p, float4 &q) {
+    uint32_t a, b, c, d, e, f, g, h;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h)
                  : "r"(taddr));
-    return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+    p = make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+    q = make_float4(__uint_as_float(e), __uint_as_float(f), __uint_as_float(g), __uint_as_float(h));
+}
+// shared-memory store of one packed pair, spelled as two 32-bit registers: with a plain `*p = v` ptxas
+// (12.9) copies every 64-bit FFMA2 result into one staging pair before its STS.64 (2 MOV per store,
+// serialised on that pair's scoreboard) -- 32 stores per exchange, 6% of the kernel's time
+__device__ __forceinline__ void sts_pair(float2 *p, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
 }
 // the loaded registers are routed through the wait so that no use can be scheduled above it
 __device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b, float4 &c, float4 &d) {
@@ -86,8 +99,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         for (int s = 0; s <= RING_S; ++s) mbar_init(&sm.mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sm.mbar[RING_S], (uint32_t)(sizeof(sm.twA) + sizeof(sm.twB)));
-        tma_load_1d(&sm.twA[0][0], prm.twA, (uint32_t)sizeof(sm.twA), &sm.mbar[RING_S]);
-        tma_load_1d(&sm.twB[0][0], prm.twB, (uint32_t)sizeof(sm.twB), &sm.mbar[RING_S]);
+        tma_load_1d(&sm.twA[0][0], prm.twAp, (uint32_t)sizeof(sm.twA), &sm.mbar[RING_S]);
+        tma_load_1d(&sm.twB[0][0], prm.twBp, (uint32_t)sizeof(sm.twB), &sm.mbar[RING_S]);
     }
     // all 512 columns: warps w and w+4 share a lane quarter, 256 columns each =
     // 16 points x [4 taps | z1 | z2 | z3 (4 floats each: re ch0, re ch1, im ch0, im ch1)]
@@ -218,12 +231,22 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                 tmem_st4(tm_pts + 16 * r + 8, make_float4(n2r.x, n2r.y, n2i.x, n2i.y));
                 tmem_st4(tm_pts + 16 * r + 12, make_float4(n3r.x, n3r.y, n3i.x, n3i.y));
             };
+            // software pipeline: the tensor-memory loads of point r+1 are issued before point r is
+            // computed, so its tcgen05.wait::ld finds them complete
+            {
+                float4 tp[2], z1[2], z2[2], z3[2];
+                tmem_ld8(tm_pts, tp[0], z1[0]);
+                tmem_ld8(tm_pts + 8, z2[0], z3[0]);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                float4 tp = tmem_ld4(tm_pts + 16 * r), z1 = tmem_ld4(tm_pts + 16 * r + 4),
-                       z2 = tmem_ld4(tm_pts + 16 * r + 8), z3 = tmem_ld4(tm_pts + 16 * r + 12);
-                tmem_wait_ld(tp, z1, z2, z3);
-                point(r, tp, z1, z2, z3);
+                for (int r = 0; r < 16; ++r) {
+                    const int c = r & 1, n = c ^ 1;
+                    tmem_wait_ld(tp[c], z1[c], z2[c], z3[c]);
+                    if (r + 1 < 16) {
+                        tmem_ld8(tm_pts + 16 * (r + 1), tp[n], z1[n]);
+                        tmem_ld8(tm_pts + 16 * (r + 1) + 8, z2[n], z3[n]);
+                    }
+                    point(r, tp[c], z1[c], z2[c], z3[c]);
+                }
             }
             if (compute) {
                 if (!tables_ready) {
@@ -232,25 +255,26 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                 }
                 dft16(v);
                 float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
-                float2 tw[4], twn[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = sm.twA[4 * b][t];
+                float4 tq[2], tqn[2];
+                tq[0] = sm.twA[0][t];
+                tq[1] = sm.twA[1][t];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = sm.twA[g + 1 + 4 * b][t];
+                        tqn[0] = sm.twA[2 * g + 2][t];
+                        tqn[1] = sm.twA[2 * g + 3][t];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k1 = g + 4 * b;
                         C2 z = v[4 * g + b];
-                        if (k1 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        xr[k1 * NT + t] = z.r;
-                        xi[k1 * NT + t] = z.i;
+                        const float4 q = tq[b >> 1];
+                        if (k1 != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
+                        sts_pair(&xr[k1 * TILE + k1B * ROWP + lo], z.r);
+                        sts_pair(&xi[k1 * TILE + k1B * ROWP + lo], z.i);
                     }
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
+                    tq[0] = tqn[0];
+                    tq[1] = tqn[1];
                 }
             }
         };
@@ -259,34 +283,35 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         auto fft_rest = [&](int buf) {
             float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = {xr[k1B * 256 + n2 * 16 + lo], xi[k1B * 256 + n2 * 16 + lo]};
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = {xr[k1B * TILE + n2 * ROWP + lo], xi[k1B * TILE + n2 * ROWP + lo]};
             dft16(v);
             __syncwarp();
             {
-                float2 tw[4], twn[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) tw[b] = sm.twB[4 * b][lo];
+                float4 tq[2], tqn[2];
+                tq[0] = sm.twB[0][lo];
+                tq[1] = sm.twB[1][lo];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g < 3) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) twn[b] = sm.twB[g + 1 + 4 * b][lo];
+                        tqn[0] = sm.twB[2 * g + 2][lo];
+                        tqn[1] = sm.twB[2 * g + 3][lo];
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int k2 = g + 4 * b;
                         C2 z = v[4 * g + b];
-                        if (k2 != 0) z = cmuls(z, tw[b].x, tw[b].y);
-                        xr[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.r;
-                        xi[k1B * 256 + k2 * 16 + (lo ^ k2)] = z.i;
+                        const float4 q = tq[b >> 1];
+                        if (k2 != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
+                        sts_pair(&xr[k1B * TILE + k2 * ROWP + lo], z.r);
+                        sts_pair(&xi[k1B * TILE + k2 * ROWP + lo], z.i);
                     }
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) tw[b] = twn[b];
+                    tq[0] = tqn[0];
+                    tq[1] = tqn[1];
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int n3 = 0; n3 < 16; ++n3) v[n3] = {xr[k1B * 256 + lo * 16 + (n3 ^ lo)], xi[k1B * 256 + lo * 16 + (n3 ^ lo)]};
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = {xr[k1B * TILE + lo * ROWP + n3], xi[k1B * TILE + lo * ROWP + n3]};
             dft16(v);
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
@@ -323,8 +348,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             for (int jj = 0; jj < 16; ++jj) {
                 const int bin = k1B + 16 * lo + 256 * perm16(jj);
                 const int sw = bin ^ lo;
-                xs[sw] = accx[jj];
-                xs[N + sw] = acca[jj];
+                sts_pair(&xs[sw], accx[jj]);
+                sts_pair(&xs[N + sw], acca[jj]);
             }
             __syncthreads();
             float2 *px = prm.part_x + (long long)seg * N;
