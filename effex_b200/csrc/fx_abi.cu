@@ -29,6 +29,7 @@ struct fx_handle {
     int logN = 0;
     int num_sms = 148;
     bool fused = false;
+    int logF = 0;     // fused kernel: frames per 4096-sample super-frame = 2^logF (nbins = 4096 >> logF)
     bool staggered = false;   // fused path uses fused_kernel_stag
     bool taps_set = false;
     cudaStream_t stream = nullptr, stream_copy = nullptr;
@@ -187,6 +188,8 @@ int ensure_parts(fx_handle *h, size_t n_segs) {
 int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
     if (P <= 0) P = h->P;
     if (h->planned_blocks == n_blocks && h->planned_P == P) return FX_OK;
+    const long long planned_P = P;
+    P = (P + (1ll << h->logF) - 1) >> h->logF;       // the kernel walks super-frames of 2^logF frames
     const long long F = n_blocks * P;
     long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
     h->h_segs.clear();
@@ -230,7 +233,7 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     FX_CUDA(h, cudaMemcpy(h->d_plan, flat.data(), n_int * sizeof(int), cudaMemcpyHostToDevice));
     h->planned_blocks = n_blocks;
-    h->planned_P = P;
+    h->planned_P = planned_P;
     return ensure_parts(h, h->h_segs.size());
 }
 
@@ -269,14 +272,23 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     prm.S = o.S; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
     prm.mean_count = o.mean_count > 0 ? o.mean_count : o.S;
     prm.halo0 = o.halo0; prm.halo1 = o.halo1;
+    prm.P = (int)o.P; prm.Psf = (int)((o.P + (1ll << h->logF) - 1) >> h->logF);
     const int grid = h->plan_grid;
     h->parts_per_block = false;
     EventPair ep{};
     rc = begin_timed(h, ep);
     if (rc) return rc;
-    if (h->staggered)
-        fx::fused4096::fused_kernel_stag<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::SmemS), h->stream>>>(prm);
-    else
+    if (h->staggered) {
+        using namespace fx::fused4096;
+        const size_t smem = sizeof(SmemS);
+        switch (h->logF) {
+            case 0: fused_kernel_stag<0><<<grid, NT, smem, h->stream>>>(prm); break;
+            case 1: fused_kernel_stag<1><<<grid, NT, smem, h->stream>>>(prm); break;
+            case 2: fused_kernel_stag<2><<<grid, NT, smem, h->stream>>>(prm); break;
+            case 3: fused_kernel_stag<3><<<grid, NT, smem, h->stream>>>(prm); break;
+            default: fused_kernel_stag<4><<<grid, NT, smem, h->stream>>>(prm); break;
+        }
+    } else
         fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
     FX_LAUNCH_CHECK(h, "fused4096");
     rc = release_sums(h);
@@ -400,7 +412,8 @@ bool fused_ok_for(const fx_handle *h, const void *a, const void *b) {
 
 int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
     const bool halo_ok = ((reinterpret_cast<uintptr_t>(o.halo0) | reinterpret_cast<uintptr_t>(o.halo1)) & 15) == 0;
-    const bool kernel_ok = h->staggered || !o.halo0;      // the lock-step kernel has no halo path
+    // halos: staggered kernel at 4096 bins only (a halo is T-1 frames, not a whole super-frame)
+    const bool kernel_ok = !o.halo0 || (h->staggered && h->logF == 0);
     if (fused_ok_for(h, d_iq0, d_iq1) && halo_ok && kernel_ok && (o.S % 8) == 0) return run_fused(h, d_iq0, d_iq1, o);
     return run_generic(h, d_iq0, d_iq1, o);
 }
@@ -568,8 +581,9 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     h->P = (int)(cfg->num_samp / cfg->nbins);
     h->logN = ilog2(cfg->nbins);
     h->num_sms = prop.multiProcessorCount;
-    h->fused = cfg->nbins == fx::fused4096::N && cfg->ntaps == fx::fused4096::T && (cfg->num_samp % 8) == 0 &&
-               !(cfg->flags & FX_FLAG_FORCE_GENERIC);
+    h->fused = cfg->nbins >= 256 && cfg->nbins <= fx::fused4096::N && cfg->ntaps == fx::fused4096::T &&
+               (cfg->num_samp % 8) == 0 && !(cfg->flags & FX_FLAG_FORCE_GENERIC);
+    h->logF = h->fused ? 12 - h->logN : 0;
     auto bail = [&](const std::string &m) { g_create_error = m; fx_destroy(h); return FX_ERR_CUDA; };
 #define CREATE_CUDA(expr)                                                        \
     do {                                                                         \
@@ -612,29 +626,45 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
             }
         CREATE_CUDA(cudaMemcpy(h->d_twA, twA.data(), twA.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaMemcpy(h->d_twB, twB.data(), twB.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        // paired copies: row 2g+h holds (tw[k], tw[k+4]) for k = g + 8h, so one 128-bit load feeds two twiddles
+        // staggered kernel: tables in stage-A/B REGISTER order, two registers per float4 (one LDS.128):
+        // row 2g+h holds the twiddles of registers j = 4g+2h and j+1.  Stage A: register j writes
+        // tile row_of(j) = frame slot * RP + k1' and carries W_NL^(t*k1'), NL = nbins; stage B:
+        // register j holds k2 = perm16(j) and carries W256^(n3*k2).
         std::vector<float4> twAp(8 * 256), twBp(8 * 16);
-        for (int g = 0; g < 4; ++g)
-            for (int hh = 0; hh < 2; ++hh) {
-                const int k = g + 8 * hh;
+        {
+            const int RP = 16 >> h->logF, NL = cfg->nbins;
+            auto wA = [&](int j, int t) {
+                const int k1p = fx::fused4096::row_of(h->logF, j) % RP;
+                const double a = -2.0 * M_PI * (double)((k1p * t) % NL) / (double)NL;
+                return make_float2((float)cos(a), (float)sin(a));
+            };
+            for (int r = 0; r < 8; ++r) {
+                const int j = 2 * r;       // = 4g + 2h for r = 2g + h
                 for (int t = 0; t < 256; ++t) {
-                    const float2 a = twA[k * 256 + t], b = twA[(k + 4) * 256 + t];
-                    twAp[(2 * g + hh) * 256 + t] = make_float4(a.x, a.y, b.x, b.y);
+                    const float2 a = wA(j, t), b = wA(j + 1, t);
+                    twAp[r * 256 + t] = make_float4(a.x, a.y, b.x, b.y);
                 }
                 for (int n3 = 0; n3 < 16; ++n3) {
-                    const float2 a = twB[k * 16 + n3], b = twB[(k + 4) * 16 + n3];
-                    twBp[(2 * g + hh) * 16 + n3] = make_float4(a.x, a.y, b.x, b.y);
+                    const float2 a = twB[fx::perm16(j) * 16 + n3], b = twB[fx::perm16(j + 1) * 16 + n3];
+                    twBp[r * 16 + n3] = make_float4(a.x, a.y, b.x, b.y);
                 }
             }
+        }
         CREATE_CUDA(cudaMalloc(&h->d_twAp, twAp.size() * sizeof(float4)));
         CREATE_CUDA(cudaMalloc(&h->d_twBp, twBp.size() * sizeof(float4)));
         CREATE_CUDA(cudaMemcpy(h->d_twAp, twAp.data(), twAp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaMemcpy(h->d_twBp, twBp.data(), twBp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::fused4096::Smem)));
-        CREATE_CUDA(cudaFuncSetAttribute(fx::fused4096::fused_kernel_stag, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(fx::fused4096::SmemS)));
-        h->staggered = !(cfg->flags & FX_FLAG_LOCKSTEP_KERNEL);
+        {
+            using namespace fx::fused4096;
+            const void *ks[5] = {(const void *)fused_kernel_stag<0>, (const void *)fused_kernel_stag<1>,
+                                 (const void *)fused_kernel_stag<2>, (const void *)fused_kernel_stag<3>,
+                                 (const void *)fused_kernel_stag<4>};
+            CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+        }
+        // the lock-step cross-check kernel exists for 4096 bins only
+        h->staggered = !(cfg->flags & FX_FLAG_LOCKSTEP_KERNEL) || h->logF != 0;
     }
 #undef CREATE_CUDA
     *out = h;

@@ -47,8 +47,8 @@ struct __align__(16) Smem {
 
 struct Segment {
     int block;       // block index within the call
-    int f0;          // first output frame (block-relative)
-    int nf;          // number of output frames
+    int f0;          // first output frame (block-relative); super-frames when nbins < 4096
+    int nf;          // number of output frames (super-frames)
     int pad;
 };
 
@@ -68,6 +68,8 @@ struct Params {
     const uint8_t *halo0, *halo1;       // streaming mode: the (T-1) frames that precede frame 0 of block 0, or NULL
     int n_segs;
     int dc_remove;
+    int P;                              // frames per block
+    int Psf;                            // super-frames per block = ceil(P / F)  (= P for 4096 bins; see fx_fused4096s.cuh)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -47,7 +47,7 @@ struct __align__(16) SmemS {
     uint32_t tmem_base;
     // TMA producer state of the current segment (written and read by thread 0 only; kept out of registers)
     const uint8_t *src0, *src1, *nsrc0, *nsrc1, *hsrc0, *hsrc1;
-    int n_ing, n_ing_next, n_halo;
+    int n_ing, n_ing_next, n_halo, g0, ng0;
 };
 
 // ---- tensor memory helpers (tcgen05; 32 lanes x 32-bit columns per warp quarter) -------------
@@ -88,7 +88,56 @@ __device__ __forceinline__ void tmem_wait_ld(float4 &a, float4 &b, float4 &c, fl
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- frame lengths below 4096 ------------------------------------------------------------------
+// LOGF > 0: a ring slot holds one SUPER-FRAME of 4096 consecutive samples = F = 2^LOGF consecutive
+// frames of NL = 4096/F bins.  A thread still owns the 16 samples t + 256 r; they are now RP = 16/F
+// positions p' = t + 256 r' of each of the F frames (r = f*RP + r').  What changes:
+//   FIR      per position r' the state is loaded once and carried in registers through the F frames;
+//   stage A  F DFTs of RP points (instead of one of 16), twiddle W_NL^(t*k1'), tile = f*RP + k1';
+//   B, C     unchanged: every tile is still one 256-point transform over t;
+//   bins     tile f*RP + k1' holds bins k1' + RP*(k2 + 16*k3) of frame f; the F frame slots are added
+//            in the segment epilogue.
+// Segments, the ring and the TMA copies count super-frames; the last super-frame of a block may hold
+// fewer than F frames (P mod F): its copy is shortened and its missing frames are not accumulated.
+__host__ __device__ constexpr int perm_rp(int RP, int jj) {
+    return RP == 16 ? perm16(jj) : RP == 8 ? (jj < 4 ? 2 * jj : 2 * (jj - 4) + 1) : jj;
+}
+// exchange-1 tile written by register j of stage A
+__host__ __device__ constexpr int row_of(int LOGF, int j) {
+    return (j / (16 >> LOGF)) * (16 >> LOGF) + perm_rp(16 >> LOGF, j % (16 >> LOGF));
+}
+// forward 8-point DFT in place; v[m] = Y[2m], v[4+m] = Y[2m+1]
+__device__ __forceinline__ void dft8(C2 *v) {
+    constexpr float R2 = 0.70710678118654752f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        const C2 s = cadd(v[n], v[n + 4]), d = csub(v[n], v[n + 4]);
+        v[n] = s;
+        v[n + 4] = d;
+    }
+    v[5] = {f2muls(f2add(v[5].r, v[5].i), R2), f2muls(f2sub(v[5].i, v[5].r), R2)};      // * W8^1
+    v[6] = {v[6].i, f2neg(v[6].r)};                                                      // * W8^2 = -i
+    v[7] = {f2muls(f2sub(v[7].i, v[7].r), R2), f2muls(f2add(v[7].r, v[7].i), -R2)};     // * W8^3
+    radix4(v[0], v[1], v[2], v[3]);
+    radix4(v[4], v[5], v[6], v[7]);
+}
+template <int RP>
+__device__ __forceinline__ void dft_small(C2 *v) {
+    if constexpr (RP == 8) dft8(v);
+    if constexpr (RP == 4) radix4(v[0], v[1], v[2], v[3]);
+    if constexpr (RP == 2) {
+        const C2 s = cadd(v[0], v[1]), d = csub(v[0], v[1]);
+        v[0] = s;
+        v[1] = d;
+    }
+}
+
+template <int LOGF>
 __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
+    constexpr int F = 1 << LOGF;        // frames per super-frame
+    constexpr int RP = 16 >> LOGF;      // positions of one frame held by a thread = stage-A radix
+    constexpr int NL = N >> LOGF;       // frame length = number of bins
+    constexpr int HSF = (T - 1 + F - 1) / F;   // super-frames of history re-ingested at a segment start
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemS &sm = *reinterpret_cast<SmemS *>(smem_raw);
     const int t = threadIdx.x;
@@ -110,8 +159,12 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm_pts = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * grp);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) tmem_st4(tm_pts + 16 * r, prm.taps[t + NT * r]);
+    for (int r = 0; r < RP; ++r) tmem_st4(tm_pts + 16 * r, prm.taps[t + NT * r]);
     tmem_wait_st();
+    // frames in the last super-frame of a block, and its copy size per channel
+    const int tail_valid = prm.P - F * (prm.Psf - 1);
+    const uint32_t tail_bytes = (uint32_t)tail_valid * (uint32_t)(2 * NL);
+    const int fslot = (t >> 4) >> (4 - LOGF);          // frame slot of this thread's tile in stages B, C
     bool tables_ready = false;
 
     const int k1B = t >> 4;
@@ -136,8 +189,9 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         }
         // first ingested frame: T-1 frames before the first output frame; before frame 0 of block 0 only
         // when the caller supplied the preceding samples (streaming mode), otherwise zero history
-        const bool use_halo = prm.halo0 != nullptr && sg.block == 0 && sg.f0 < T - 1;
-        const int g0 = (use_halo || sg.f0 - (T - 1) > 0) ? sg.f0 - (T - 1) : 0;
+        // (segments count super-frames; the host passes halos only when F == 1)
+        const bool use_halo = prm.halo0 != nullptr && sg.block == 0 && sg.f0 < HSF;
+        const int g0 = (use_halo || sg.f0 - HSF > 0) ? sg.f0 - HSF : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
         if (t == 0) {
             // the segment after this one (same CTA): its first frames are prefetched during our last ones
@@ -145,7 +199,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             const bool have_next = nseg < seg_end && n_ing >= RING_S;
             Segment ng = sg;
             if (have_next) ng = prm.segs[nseg];
-            const int ng0 = ng.f0 - (T - 1) > 0 ? ng.f0 - (T - 1) : 0;
+            const int ng0 = ng.f0 - HSF > 0 ? ng.f0 - HSF : 0;
             sm.src0 = b0 + (long long)g0 * FRAME_BYTES;        // ingest item j reads src + j*FRAME_BYTES ...
             sm.src1 = b1 + (long long)g0 * FRAME_BYTES;
             sm.n_halo = g0 < 0 ? -g0 : 0;                      // ... except the first n_halo items: halo frames
@@ -153,15 +207,18 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             sm.hsrc1 = prm.halo1 + (long long)(T - 1 + g0) * FRAME_BYTES;
             sm.nsrc0 = prm.iq0 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
             sm.nsrc1 = prm.iq1 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
+            sm.g0 = g0;
+            sm.ng0 = ng0;
             sm.n_ing = n_ing;
             sm.n_ing_next = have_next ? ng.f0 + ng.nf - ng0 : 0;
             const int pre = n_ing < RING_S ? n_ing : RING_S;
             for (int j = already; j < pre; ++j) {
                 const uint32_t s = (ring_cnt + j) % RING_S;
-                mbar_expect_tx(&sm.mbar[s], 2 * FRAME_BYTES);
+                const uint32_t nb = (g0 + j == prm.Psf - 1) ? tail_bytes : (uint32_t)FRAME_BYTES;
+                mbar_expect_tx(&sm.mbar[s], 2 * nb);
                 const bool hal = j < sm.n_halo;
-                tma_load_1d(&sm.raw[s][0][0], (hal ? sm.hsrc0 : sm.src0) + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
-                tma_load_1d(&sm.raw[s][1][0], (hal ? sm.hsrc1 : sm.src1) + (long long)j * FRAME_BYTES, FRAME_BYTES, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][0][0], (hal ? sm.hsrc0 : sm.src0) + (long long)j * FRAME_BYTES, nb, &sm.mbar[s]);
+                tma_load_1d(&sm.raw[s][1][0], (hal ? sm.hsrc1 : sm.src1) + (long long)j * FRAME_BYTES, nb, &sm.mbar[s]);
             }
             already = 0;
         }
@@ -171,19 +228,22 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
             const int jn = j + RING_S;
             const int ni = sm.n_ing;
             const uint8_t *s0 = nullptr, *s1 = nullptr;
+            uint32_t nb = (uint32_t)FRAME_BYTES;
             if (jn < ni) {
+                if (sm.g0 + jn == prm.Psf - 1) nb = tail_bytes;
                 const bool hal = jn < sm.n_halo;
                 s0 = (hal ? sm.hsrc0 : sm.src0) + (long long)jn * FRAME_BYTES;
                 s1 = (hal ? sm.hsrc1 : sm.src1) + (long long)jn * FRAME_BYTES;
             } else if (jn - ni < sm.n_ing_next) {
                 s0 = sm.nsrc0 + (long long)(jn - ni) * FRAME_BYTES;
                 s1 = sm.nsrc1 + (long long)(jn - ni) * FRAME_BYTES;
+                if (sm.ng0 + jn - ni == prm.Psf - 1) nb = tail_bytes;
                 already = jn - ni + 1;
             }
             if (s0) {
-                mbar_expect_tx(&sm.mbar[slot], 2 * FRAME_BYTES);
-                tma_load_1d(&sm.raw[slot][0][0], s0, FRAME_BYTES, &sm.mbar[slot]);
-                tma_load_1d(&sm.raw[slot][1][0], s1, FRAME_BYTES, &sm.mbar[slot]);
+                mbar_expect_tx(&sm.mbar[slot], 2 * nb);
+                tma_load_1d(&sm.raw[slot][0][0], s0, nb, &sm.mbar[slot]);
+                tma_load_1d(&sm.raw[slot][1][0], s1, nb, &sm.mbar[slot]);
             }
         };
 
@@ -197,7 +257,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         // zero FIR state: a segment either starts a block (zero history is the reference's semantics)
         // or first re-ingests the T-1 frames before its first output frame
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
+        for (int r = 0; r < RP; ++r) {
             tmem_st4(tm_pts + 16 * r + 4, make_float4(0.f, 0.f, 0.f, 0.f));
             tmem_st4(tm_pts + 16 * r + 8, make_float4(0.f, 0.f, 0.f, 0.f));
             tmem_st4(tm_pts + 16 * r + 12, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -219,33 +279,45 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                 const uint32_t b = sm.raw[slot][1][t + NT * r];
                 cur[r] = __byte_perm(a, b, 0x5410);               // (I0,Q0,I1,Q1)
             }
-            auto point = [&](int r, const float4 &tp, const float4 &z1, const float4 &z2, const float4 &z3) {
-                const uint32_t w = cur[r];
-                const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
-                const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
-                v[r] = {f2fmas(yr, tp.x, f2(z1.x, z1.y)), f2fmas(yi, tp.x, f2(z1.z, z1.w))};
-                const float2 n1r = f2fmas(yr, tp.y, f2(z2.x, z2.y)), n1i = f2fmas(yi, tp.y, f2(z2.z, z2.w));
-                const float2 n2r = f2fmas(yr, tp.z, f2(z3.x, z3.y)), n2i = f2fmas(yi, tp.z, f2(z3.z, z3.w));
-                const float2 n3r = f2muls(yr, tp.w), n3i = f2muls(yi, tp.w);
-                tmem_st4(tm_pts + 16 * r + 4, make_float4(n1r.x, n1r.y, n1i.x, n1i.y));
-                tmem_st4(tm_pts + 16 * r + 8, make_float4(n2r.x, n2r.y, n2i.x, n2i.y));
-                tmem_st4(tm_pts + 16 * r + 12, make_float4(n3r.x, n3r.y, n3i.x, n3i.y));
+            // position rp of every frame f of the super-frame: sample r = f*RP + rp, taps tp, state z1..z3
+            // (re ch0, re ch1, im ch0, im ch1) carried through the F frames; out = t0*y + z1
+            auto position = [&](int rp, const float4 &tp, const float4 &z1, const float4 &z2, const float4 &z3) {
+                float2 s1r = f2(z1.x, z1.y), s1i = f2(z1.z, z1.w);
+                float2 s2r = f2(z2.x, z2.y), s2i = f2(z2.z, z2.w);
+                float2 s3r = f2(z3.x, z3.y), s3i = f2(z3.z, z3.w);
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    const int r = f * RP + rp;
+                    const uint32_t w = cur[r];
+                    const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
+                    const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
+                    v[r] = {f2fmas(yr, tp.x, s1r), f2fmas(yi, tp.x, s1i)};
+                    s1r = f2fmas(yr, tp.y, s2r);
+                    s1i = f2fmas(yi, tp.y, s2i);
+                    s2r = f2fmas(yr, tp.z, s3r);
+                    s2i = f2fmas(yi, tp.z, s3i);
+                    s3r = f2muls(yr, tp.w);
+                    s3i = f2muls(yi, tp.w);
+                }
+                tmem_st4(tm_pts + 16 * rp + 4, make_float4(s1r.x, s1r.y, s1i.x, s1i.y));
+                tmem_st4(tm_pts + 16 * rp + 8, make_float4(s2r.x, s2r.y, s2i.x, s2i.y));
+                tmem_st4(tm_pts + 16 * rp + 12, make_float4(s3r.x, s3r.y, s3i.x, s3i.y));
             };
-            // software pipeline: the tensor-memory loads of point r+1 are issued before point r is
-            // computed, so its tcgen05.wait::ld finds them complete
+            // software pipeline: the tensor-memory loads of position rp+1 are issued before position rp
+            // is computed, so its tcgen05.wait::ld finds them complete
             {
                 float4 tp[2], z1[2], z2[2], z3[2];
                 tmem_ld8(tm_pts, tp[0], z1[0]);
                 tmem_ld8(tm_pts + 8, z2[0], z3[0]);
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int c = r & 1, n = c ^ 1;
+                for (int rp = 0; rp < RP; ++rp) {
+                    const int c = rp & 1, n = c ^ 1;
                     tmem_wait_ld(tp[c], z1[c], z2[c], z3[c]);
-                    if (r + 1 < 16) {
-                        tmem_ld8(tm_pts + 16 * (r + 1), tp[n], z1[n]);
-                        tmem_ld8(tm_pts + 16 * (r + 1) + 8, z2[n], z3[n]);
+                    if (rp + 1 < RP) {
+                        tmem_ld8(tm_pts + 16 * (rp + 1), tp[n], z1[n]);
+                        tmem_ld8(tm_pts + 16 * (rp + 1) + 8, z2[n], z3[n]);
                     }
-                    point(r, tp[c], z1[c], z2[c], z3[c]);
+                    position(rp, tp[c], z1[c], z2[c], z3[c]);
                 }
             }
             if (compute) {
@@ -253,7 +325,12 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                     mbar_wait(&sm.mbar[RING_S], 0);
                     tables_ready = true;
                 }
-                dft16(v);
+                if constexpr (RP == 16) {
+                    dft16(v);
+                } else {
+#pragma unroll
+                    for (int f = 0; f < F; ++f) dft_small<RP>(&v[f * RP]);
+                }
                 float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
                 float4 tq[2], tqn[2];
                 tq[0] = sm.twA[0][t];
@@ -266,12 +343,12 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                     }
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int k1 = g + 4 * b;
+                        const int row = row_of(LOGF, 4 * g + b);      // tile = frame slot * RP + k1'
                         C2 z = v[4 * g + b];
                         const float4 q = tq[b >> 1];
-                        if (k1 != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
-                        sts_pair(&xr[k1 * TILE + k1B * ROWP + lo], z.r);
-                        sts_pair(&xi[k1 * TILE + k1B * ROWP + lo], z.i);
+                        if (row % RP != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
+                        sts_pair(&xr[row * TILE + k1B * ROWP + lo], z.r);
+                        sts_pair(&xi[row * TILE + k1B * ROWP + lo], z.i);
                     }
                     tq[0] = tqn[0];
                     tq[1] = tqn[1];
@@ -280,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
         };
 
         // ---- stages B, C and the X-engine of the frame held in exchange buffer `buf` ---------------
-        auto fft_rest = [&](int buf) {
+        auto fft_rest = [&](int buf, int nv) {
             float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) v[n2] = {xr[k1B * TILE + n2 * ROWP + lo], xi[k1B * TILE + n2 * ROWP + lo]};
@@ -313,12 +390,14 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
 #pragma unroll
             for (int n3 = 0; n3 < 16; ++n3) v[n3] = {xr[k1B * TILE + lo * ROWP + n3], xi[k1B * TILE + lo * ROWP + n3]};
             dft16(v);
+            if (LOGF == 0 || fslot < nv) {        // frame slots beyond a block's last frame hold no data
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
-                accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
-                accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
-                acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+                for (int jj = 0; jj < 16; ++jj) {
+                    const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
+                    accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
+                    accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
+                    acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+                }
             }
         };
 
@@ -333,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
                 if (half == grp) {
                     if (s < n_ing) fir_stage_a(s, s >= j0, (s - j0) & 1);
                 } else {
-                    if (q >= 0) fft_rest(q & 1);
+                    if (q >= 0) fft_rest(q & 1, (sg.f0 + q == prm.Psf - 1) ? tail_valid : F);
                 }
             }
             __syncthreads();
@@ -343,23 +422,31 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
 
         // ---- segment epilogue (both exchange buffers are free after the last barrier) ----------------
         {
-            float2 *xs = &sm.Xr[0][0];                          // cross in Xr[0], autos in Xr[1]
+            float2 *xs = &sm.Xr[0][0];                          // cross in xs[0..N), autos in xs[N..2N)
+            // staging index = frame slot * NL + bin; bin = k1' + RP*(k2 + 16*k3) with k2 = lo, k3 = perm16(jj)
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-                const int bin = k1B + 16 * lo + 256 * perm16(jj);
-                const int sw = bin ^ lo;
+                const int idx = fslot * NL + (k1B & (RP - 1)) + RP * lo + 16 * RP * perm16(jj);
+                const int sw = idx ^ ((idx >> 4) & 15);
                 sts_pair(&xs[sw], accx[jj]);
                 sts_pair(&xs[N + sw], acca[jj]);
             }
             __syncthreads();
-            float2 *px = prm.part_x + (long long)seg * N;
-            float2 *pa = prm.part_a + (long long)seg * N;
+            float2 *px = prm.part_x + (long long)seg * NL;
+            float2 *pa = prm.part_a + (long long)seg * NL;
 #pragma unroll
-            for (int q = 0; q < N / NT; ++q) {
+            for (int q = 0; q < NL / NT; ++q) {
                 const int o = t + NT * q;
-                const int sw = o ^ ((o >> 4) & 15);
-                px[o] = xs[sw];
-                pa[o] = xs[N + sw];
+                float2 sx = f2(0.f, 0.f), sa = f2(0.f, 0.f);
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    const int idx = f * NL + o;
+                    const int sw = idx ^ ((idx >> 4) & 15);
+                    sx = f2add(sx, xs[sw]);
+                    sa = f2add(sa, xs[N + sw]);
+                }
+                px[o] = sx;
+                pa[o] = sa;
             }
             __syncthreads();       // the next segment's first exchange stores must not overtake these reads
         }

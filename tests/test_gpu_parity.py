@@ -187,6 +187,39 @@ def test_generic_shapes_vs_oracle(S, N, T):
     eng.close()
 
 
+# --------------------------------------------------------------------------
+# nbins < 4096 on the fused kernel: F = 4096/N frames per 4096-sample super-frame.
+# Shapes cover whole super-frames, a partial last super-frame (P mod F != 0), a block shorter than
+# one super-frame, many short blocks (segments that end inside a CTA's run) and S not a multiple of N.
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("S,N,nb", [(2**16, 2048, 3), (2**16, 1024, 3), (2**15, 512, 3), (2**14, 256, 3),
+                                    (319488, 1024, 2), (7 * 1024, 1024, 5), (3 * 1024, 1024, 4),
+                                    (11 * 256 + 8, 256, 6), (5 * 2048, 2048, 9), (2**13, 1024, 700)])
+def test_fused_small_nbins_vs_oracle_and_generic(S, N, nb):
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=3, dc0=0.013 - 0.02j, dc1=-0.006 + 0.004j, seed=5)
+    bw, fc, tau = 2.4e6, 1.4204e9, 3 / 2.4e6
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    assert eng.fused
+    eng.set_delay(bw, fc, tau)
+    x, a0, a1 = eng.process(dev(raw0), dev(raw1), nb, autos=True)
+    x, a0, a1 = x.cpu().numpy(), a0.cpu().numpy(), a1.cpu().numpy()
+    gen = FxEngine(S, N, 4, max_blocks=nb, force_generic=True)
+    assert not gen.fused
+    gen.set_delay(bw, fc, tau)
+    xg, g0, g1 = gen.process(dev(raw0), dev(raw1), nb, autos=True)
+    xg, g0, g1 = xg.cpu().numpy(), g0.cpu().numpy(), g1.cpu().numpy()
+    check = range(nb) if nb <= 9 else [0, 1, nb // 2, nb - 2, nb - 1]
+    ref = {b: orc.process_recording_u8(raw0, raw1, S, N, bw, fc, tau, 4, b, 1)[0] for b in check}
+    for b in check:
+        assert_close(x[b], ref[b], what=f"S={S} N={N} block {b} fused vs oracle")
+        r0, r1 = oracle_autos(raw0, raw1, S, N, b)
+        assert np.abs(a0[b] - r0).max() <= TOL * r0.max() and np.abs(a1[b] - r1).max() <= TOL * r1.max()
+    # every block against the generic kernels (independent code, same arithmetic type)
+    assert np.abs(x - xg).max() <= 2e-6 * np.abs(xg).max()
+    assert np.abs(a0 - g0).max() <= 2e-6 * g0.max() and np.abs(a1 - g1).max() <= 2e-6 * g1.max()
+    eng.close(); gen.close()
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_golden_reference_fixture(golden_dir, tag):
     """Fixtures made by running the reference's own effex.py (tests/golden/make_golden.py)."""

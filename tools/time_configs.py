@@ -22,7 +22,10 @@ def run(name, S, N, nb, reps=5):
 
 run("C1 canonical", 262144, 4096, 550)
 run("C5 short integrations", 319488, 1024, 600)
-run("N=2048", 262144, 2048, 200)
+run("N=1024 S=2^18", 262144, 1024, 550)
+run("N=2048", 262144, 2048, 550)
+run("N=512", 262144, 512, 550)
+run("N=256", 262144, 256, 550)
 run("C3 hi-res line", 2**24, 65536, 2)
 n = 262144
 eng = FxEngine(n, 4096, 4, max_blocks=92)
