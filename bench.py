@@ -336,6 +336,13 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         per_launch_ms = kern_ms / max(kern_n, 1)
         achieved = ALG_BYTES_PER_BLOCK * N_BLOCKS / (per_launch_ms * 1e-3) / 1e9 if kern_n else None
+        # FP32-pipe view of the same kernel (DESIGN.md "roofline"): per frame and thread the SASS holds 776
+        # packed (FFMA2/FADD2/FMUL2, 2 issue cycles of the FMA pipe per warp) and 64 scalar FFMA; one SM
+        # sub-partition runs 2 of the CTA's 8 warps.
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        frames = N_BLOCKS * (S // N)
+        fma_cycles = (776 * 2 + 64) * 2 * (frames / 148.0)
+        fp32_min_ms = fma_cycles / (sm_mhz * 1e3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
@@ -352,7 +359,11 @@ def run_ours(args):
                          "traffic": traffic_per_launch(), "peak_source": peak_src,
                          "kernel_ms_per_launch": per_launch_ms, "kernel_ms_isolated": kernel_ms_isolated, "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_BLOCK * N_BLOCKS,
-                         "note": "FP32-pipe bound, not HBM bound: see DESIGN.md (roofline). kernel_ms_per_launch is event-bracketed inside the timed region and includes queueing behind the overlapped pre-pass of the next step; kernel_ms_isolated is the same kernel launched alone"},
+                         "fp32_pipe": {"frac": fp32_min_ms / per_launch_ms if kern_n else None,
+                                       "frac_isolated": fp32_min_ms / kernel_ms_isolated if kernel_ms_isolated else None,
+                                       "fma_pipe_ms_at_full_issue": fp32_min_ms,
+                                       "basis": "SASS FMA-pipe issue cycles per frame (776 packed x2 + 64 scalar per thread) at the sampled SM clock, 148 SMs"},
+                         "note": "FP32-pipe bound, not HBM bound: see DESIGN.md (roofline). kernel_ms_per_launch is event-bracketed inside the timed region, where the byte-sum pre-pass of the next step runs on the same SMs underneath this kernel; kernel_ms_isolated is the same kernel launched alone"},
             "clocks": clocks,
         }
         if world == 1:

@@ -132,8 +132,14 @@ __device__ __forceinline__ void dft_small(C2 *v) {
     }
 }
 
+// 232 registers x 256 threads leave room on the SM for two CTAs of the byte-sum pre-pass (128 threads x
+// 32 registers): the pre-pass of call k+1 (HBM-bound) then runs underneath this kernel (FP32-bound) of
+// call k instead of after it.  ptxas needs 219 registers at this cap and does not spill.
+#ifndef FX_MAXNREG
+#define FX_MAXNREG 232
+#endif
 template <int LOGF>
-__global__ void __launch_bounds__(NT, 1) fused_kernel_stag(const Params prm) {
+__global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
     constexpr int F = 1 << LOGF;        // frames per super-frame
     constexpr int RP = 16 >> LOGF;      // positions of one frame held by a thread = stage-A radix
     constexpr int NL = N >> LOGF;       // frame length = number of bins

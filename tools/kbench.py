@@ -18,11 +18,14 @@ eng = FxEngine(S, N, 4, max_blocks=NB)
 out = (torch.empty((NB, N), dtype=torch.complex64, device="cuda"), None, None)
 for _ in range(3): eng.process(d0, d1, NB, out=out)
 eng.sync(); eng.reset_counters(); eng.enable_timing(True)
+import time
+t0 = time.perf_counter()
 for _ in range(10): eng.process(d0, d1, NB, out=out)
 eng.sync()
+step_us = (time.perf_counter() - t0) / 10 * 1e6
 ms, n = eng.dominant_kernel_time()
 chk = float(out[0].abs().sum().item())
-print("%%-40s fused kernel %%8.1f us/launch   %%9.0f Msamples/s (kernel only)  checksum %%.6e" %% (os.path.basename(os.environ.get("EFFEX_FX_LIB","default")), 1e3*ms/n, NB*S/(ms/n*1e-3)/1e6, chk))
+print("%%-28s fused kernel %%7.1f us/launch %%8.0f Msamples/s (kernel only)   step %%7.1f us %%8.0f Msamples/s  checksum %%.6e" %% (os.path.basename(os.environ.get("EFFEX_FX_LIB","default")), 1e3*ms/n, NB*S/(ms/n*1e-3)/1e6, step_us, NB*S/step_us, chk))
 ''' % ROOT
 
 for lib in sys.argv[1:]:
