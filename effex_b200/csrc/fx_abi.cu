@@ -317,6 +317,33 @@ __global__ void phase_post_kernel(float2 *x, int N, long long total) {
     x[i] = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
 }
 
+// Transform of `rows` rows of length M = 2^logM > 4096 in global memory: ceil(logM/8) radix-R Stockham
+// passes (R <= 256) ping-ponging between buf and tmp.  Returns the buffer that holds the result.
+int stockham_passes(fx_handle *h, float2 *buf, float2 *tmp, long long M, long long rows, int inverse,
+                    float2 **result) {
+    const int logM = ilog2(M);
+    const int npass = (logM + 7) / 8;
+    float2 *src = buf, *dst = tmp;
+    long long Ns = 1;
+    for (int p = 0; p < npass; ++p) {
+        const int bits = logM / npass + (p < logM % npass ? 1 : 0);
+        const long long R = 1ll << bits;
+        const size_t smem = (2 * (size_t)R * (fx::generic::kPassJ + 1) + (size_t)R / 2) * sizeof(float2);
+        const int threads = (int)std::min<long long>(512, R * fx::generic::kPassJ / 2);
+        for (long long r0 = 0; r0 < rows; r0 += 65535) {
+            const long long nr = std::min<long long>(65535, rows - r0);
+            dim3 grid((unsigned)(M / R / fx::generic::kPassJ), (unsigned)nr);
+            fx::generic::stockham_radix_pass_kernel<<<grid, threads, smem, h->stream>>>(src + r0 * M, dst + r0 * M, M, Ns,
+                                                                                      bits, inverse);
+            FX_LAUNCH_CHECK(h, "stockham_radix_pass");
+        }
+        Ns *= R;
+        std::swap(src, dst);
+    }
+    *result = src;
+    return FX_OK;
+}
+
 // batched FFT of `rows` rows of length N held in buf; tmp is scratch of the same size.
 // Result is left in buf.
 int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, int inverse, int phase_post,
@@ -335,13 +362,9 @@ int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, i
             FX_LAUNCH_CHECK(h, "fft_rows");
         }
     } else {
-        float2 *src = buf, *dst = tmp;
-        for (int s = 0; s < logN; ++s) {
-            dim3 grid((unsigned)((N / 2 + 255) / 256), (unsigned)rows);
-            fx::generic::stockham_pass_kernel<<<grid, 256, 0, h->stream>>>(src, dst, N, 1ll << s, inverse);
-            FX_LAUNCH_CHECK(h, "stockham_pass");
-            std::swap(src, dst);
-        }
+        float2 *src = nullptr;
+        rc = stockham_passes(h, buf, tmp, N, rows, inverse, &src);
+        if (rc) return rc;
         if (src != buf)
             FX_CUDA(h, cudaMemcpyAsync(buf, src, sizeof(float2) * (size_t)N * rows, cudaMemcpyDeviceToDevice, h->stream));
         if (phase_post) {
@@ -358,7 +381,7 @@ int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, 
                       const PassOpts &o) {
     const int N = h->cfg.nbins, T = h->cfg.ntaps, P = (int)o.P;
     const long long S = o.S;
-    dim3 grid((N + 255) / 256, P, (unsigned)nb);
+    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, (unsigned)nb);
     fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
                                                                   h->d_sums + 4 * b0, 4, h->cfg.dc_remove, h->d_g0,
                                                                   b0 == 0 ? o.halo0 : nullptr, o.mean_count);
@@ -379,7 +402,8 @@ int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, 
 }
 
 int run_generic(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
-    if (o.P > 65535) return fail(h, FX_ERR_UNSUPPORTED, "generic kernels: more than 65535 frames in one unit");
+    if (o.P > 65535ll * fx::generic::kFirFrames)
+        return fail(h, FX_ERR_UNSUPPORTED, "generic kernels: more than 524280 frames in one unit");
     int rc = prepare_sums(h, d_iq0, d_iq1, o);
     if (rc) return rc;
     rc = ensure_parts(h, (size_t)o.units);
@@ -478,14 +502,10 @@ int ensure_lag(fx_handle *h, long long M) {
 
 // in-place (result in buf) global-memory FFT of `rows` rows of length M
 int fft_global(fx_handle *h, float2 *buf, float2 *tmp, long long M, int rows, int inverse) {
-    const int logM = ilog2(M);
-    float2 *src = buf, *dst = tmp;
-    for (int s = 0; s < logM; ++s) {
-        dim3 grid((unsigned)((M / 2 + 255) / 256), (unsigned)rows);
-        fx::generic::stockham_pass_kernel<<<grid, 256, 0, h->stream>>>(src, dst, M, 1ll << s, inverse);
-        FX_LAUNCH_CHECK(h, "stockham_pass");
-        std::swap(src, dst);
-    }
+    if (M <= 4096) return fft_batched(h, buf, tmp, (int)M, rows, inverse, 0, false);   // one CTA per row
+    float2 *src = nullptr;
+    int rc = stockham_passes(h, buf, tmp, M, rows, inverse, &src);
+    if (rc) return rc;
     if (src != buf)
         FX_CUDA(h, cudaMemcpyAsync(buf, src, sizeof(float2) * (size_t)M * rows, cudaMemcpyDeviceToDevice, h->stream));
     return FX_OK;
@@ -609,6 +629,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     h->d_sums = h->d_sums_set[0];
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      2 * 4096 * (int)sizeof(float2)));
+    CREATE_CUDA(cudaFuncSetAttribute(fx::generic::stockham_radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * 256 * (fx::generic::kPassJ + 1) + 128) * (int)sizeof(float2)));
     if (h->fused) {
         CREATE_CUDA(cudaMalloc(&h->d_taps4, fx::fused4096::N * sizeof(float4)));
         CREATE_CUDA(cudaMalloc(&h->d_twA, 16 * 256 * sizeof(float2)));
@@ -880,7 +902,7 @@ int fx_pfb_c64(fx_handle *h, const float *d_x, float *d_frames) {
     const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
     int rc = ensure_generic(h, (size_t)P * N);
     if (rc) return rc;
-    dim3 grid((N + 255) / 256, P, 1);
+    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);
     fx::generic::pfb_fir_kernel<false><<<grid, 256, 0, h->stream>>>(d_x, h->cfg.num_samp, N, T, P, h->d_taps_c,
                                                                    nullptr, 0, 0, out);
@@ -898,7 +920,7 @@ int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames) {
     if (rc) return rc;
     rc = launch_sums(h, d_iq, d_iq, 1);
     if (rc) return rc;
-    dim3 grid((N + 255) / 256, P, 1);
+    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);
     fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, N, T, P, h->d_taps_u8,
                                                                   h->d_sums, 4, h->cfg.dc_remove, out);

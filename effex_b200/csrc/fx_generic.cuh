@@ -84,8 +84,10 @@ __global__ void __maxnreg__(32) block_sums_kernel(const uint8_t *__restrict__ iq
 // ---------------------------------------------------------------------------
 // PFB FIR, any T <= 32, any N.   w[b][i][p] = sum_{k<=min(i,T-1)} taps[k][p] * x[(i-k)N + p]
 // taps[k][p] = h[kN + N-1-p] (already reversed; the u8 variant is pre-scaled by 1/127.5)
-// grid = (ceil(N/256), P, n_blocks)
+// grid = (ceil(N/256), ceil(P/kFirFrames), n_blocks): a thread produces kFirFrames consecutive frames of
+// one branch p (independent loads of several frames in flight; means and index set-up paid once)
 // ---------------------------------------------------------------------------
+constexpr int kFirFrames = 8;
 template <bool U8>
 __global__ void __launch_bounds__(256) pfb_fir_kernel(const void *__restrict__ in, long long S, int N, int T, int P,
                                                       const float *__restrict__ taps,
@@ -93,40 +95,48 @@ __global__ void __launch_bounds__(256) pfb_fir_kernel(const void *__restrict__ i
                                                       int dc_remove, float2 *__restrict__ w,
                                                       const void *__restrict__ halo = nullptr, long long mean_count = 0) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, b = blockIdx.z;
-    if (p >= N) return;
-    float mi = 0.f, mq = 0.f;
-    if (U8) {
+    const int i0 = blockIdx.y * kFirFrames, b = blockIdx.z;
+    // block means: float64 division once per CTA, not once per thread
+    __shared__ float s_mean[2];
+    if (U8 && threadIdx.x == 0) {
         if (dc_remove) {
             const double den = (double)(mean_count > 0 ? mean_count : S);
-            mi = (float)((double)sums[(long long)b * sum_stride] / den);
-            mq = (float)((double)sums[(long long)b * sum_stride + 1] / den);
+            s_mean[0] = (float)((double)sums[(long long)b * sum_stride] / den);
+            s_mean[1] = (float)((double)sums[(long long)b * sum_stride + 1] / den);
         } else {
-            mi = mq = 127.5f;
+            s_mean[0] = s_mean[1] = 127.5f;
         }
     }
-    float ar = 0.f, ai = 0.f;
-    // zero history before frame 0 -- unless the caller supplied the T-1 preceding frames (streaming mode)
-    const int kmax = (i < T - 1 && !(halo && b == 0)) ? i : T - 1;
-    for (int k = 0; k <= kmax; ++k) {
-        long long s = (long long)b * S + (long long)(i - k) * N + p;
-        const void *src = in;
-        if (i - k < 0) { src = halo; s = (long long)(i - k + T - 1) * N + p; }
-        float xr, xi;
-        if (U8) {
-            const uchar2 q = reinterpret_cast<const uchar2 *>(src)[s];
-            xr = (float)q.x - mi;
-            xi = (float)q.y - mq;
-        } else {
-            const float2 q = reinterpret_cast<const float2 *>(src)[s];
-            xr = q.x;
-            xi = q.y;
+    if (U8) __syncthreads();
+    if (p >= N) return;
+    const float mi = U8 ? s_mean[0] : 0.f, mq = U8 ? s_mean[1] : 0.f;
+    const bool have_halo = halo && b == 0;
+#pragma unroll 4
+    for (int i = i0; i < i0 + kFirFrames; ++i) {
+        if (i >= P) break;
+        float ar = 0.f, ai = 0.f;
+        // zero history before frame 0 -- unless the caller supplied the T-1 preceding frames (streaming mode)
+        const int kmax = (i < T - 1 && !have_halo) ? i : T - 1;
+        for (int k = 0; k <= kmax; ++k) {
+            long long s = (long long)b * S + (long long)(i - k) * N + p;
+            const void *src = in;
+            if (i - k < 0) { src = halo; s = (long long)(i - k + T - 1) * N + p; }
+            float xr, xi;
+            if (U8) {
+                const uchar2 q = reinterpret_cast<const uchar2 *>(src)[s];
+                xr = (float)q.x - mi;
+                xi = (float)q.y - mq;
+            } else {
+                const float2 q = reinterpret_cast<const float2 *>(src)[s];
+                xr = q.x;
+                xi = q.y;
+            }
+            const float h = taps[(long long)k * N + p];
+            ar = fmaf(h, xr, ar);
+            ai = fmaf(h, xi, ai);
         }
-        const float h = taps[(long long)k * N + p];
-        ar = fmaf(h, xr, ar);
-        ai = fmaf(h, xi, ai);
+        w[((long long)b * P + i) * N + p] = make_float2(ar, ai);
     }
-    w[((long long)b * P + i) * N + p] = make_float2(ar, ai);
 }
 
 // ---------------------------------------------------------------------------
@@ -173,26 +183,82 @@ __global__ void __launch_bounds__(512) fft_rows_kernel(const float2 *__restrict_
     }
 }
 
-// One radix-2 Stockham pass over global memory (any length M = 2^m, batch rows
-// of length M).  Used for transforms that do not fit one CTA: the 2n-point
-// lag-search FFTs and N > 4096 channelizers.   grid = (M/2/256, batch)
-__global__ void __launch_bounds__(256) stockham_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
-                                                            long long M, long long Ns, int inverse) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long half = M >> 1;
-    if (j >= half) return;
+// One radix-R Stockham autosort pass over global memory, R = 2^logR <= 256 (any length M = 2^m, batch
+// rows of length M).  For j in [0, M/R), k = j mod Ns:
+//     out[(j-k)*R + k + c*Ns] = sum_r W_R^(r*c) * W_(R*Ns)^(r*k) * in[j + r*M/R]
+// A CTA takes J consecutive j (R*J points): loads them with the inter-pass twiddle applied, runs the
+// R-point transforms of its J columns as radix-2 autosort stages in shared memory, and stores.  A
+// transform of 2^16 points is 2 passes over HBM, of 2^19 points 3 (a radix-2 pass per stage was 16 / 19).
+// Used for transforms that do not fit one CTA: the 2n-point lag-search FFTs and N > 4096 channelizers.
+// grid = (M/R/J, batch), dynamic smem = (2*R*(J+1) + R/2)*sizeof(float2)
+constexpr int kPassJ = 16;
+__global__ void __launch_bounds__(512) stockham_radix_pass_kernel(const float2 *__restrict__ in,
+                                                                  float2 *__restrict__ out, long long M,
+                                                                  long long Ns, int logR, int inverse) {
+    constexpr int J = kPassJ, JP = J + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = 1 << logR;
+    float2 *A = reinterpret_cast<float2 *>(smem_raw);
+    float2 *B = A + R * JP;
+    const long long stride = M >> logR;
+    const long long j0 = (long long)blockIdx.x * J;
     const float2 *src = in + (long long)blockIdx.y * M;
     float2 *dst = out + (long long)blockIdx.y * M;
-    const long long k = j & (Ns - 1);
-    float sn, cs;
-    // k/Ns in double so that very long transforms keep exact twiddle arguments
-    sincospif((float)((inverse ? 1.0 : -1.0) * (double)k / (double)Ns), &sn, &cs);
-    const float2 v0 = src[j];
-    const float2 a = src[j + half];
-    const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
-    const long long j0 = ((j - k) << 1) + k;
-    dst[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-    dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+    const float sgn = inverse ? 1.f : -1.f;
+    const float inv_span = 1.f / (float)((long long)R * Ns);       // power of two: r*k*inv_span is exact
+    for (int e = threadIdx.x; e < R * J; e += blockDim.x) {
+        const int r = e / J, jj = e % J;
+        const long long j = j0 + jj;
+        float2 v = src[j + r * stride];
+        const long long k = j & (Ns - 1);
+        if (k != 0 && r != 0) {
+            float sn, cs;
+            sincospif(sgn * 2.f * (float)(r * k) * inv_span, &sn, &cs);
+            v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+        }
+        A[r * JP + jj] = v;
+    }
+    // W_R^i, i < R/2, once per CTA: stage s uses W_(2 ns)^kk = W_R^(kk * R/(2 ns))
+    float2 *tw = B + R * JP;
+    const int half = R >> 1;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        float sn, cs;
+        sincospif(sgn * (float)i / (float)half, &sn, &cs);
+        tw[i] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    for (int s = 0; s < logR; ++s) {
+        const int ns = 1 << s;
+        for (int e = threadIdx.x; e < half * J; e += blockDim.x) {
+            const int b = e / J, jj = e % J;
+            const int kk = b & (ns - 1);
+            const float2 wv = tw[kk << (logR - 1 - s)];
+            const float cs = wv.x, sn = wv.y;
+            const float2 v0 = A[b * JP + jj];
+            const float2 a = A[(b + half) * JP + jj];
+            const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
+            const int o = ((b - kk) << 1) + kk;
+            B[o * JP + jj] = make_float2(v0.x + v1.x, v0.y + v1.y);
+            B[(o + ns) * JP + jj] = make_float2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        float2 *t = A; A = B; B = t;
+    }
+    if (Ns < J) {
+        // first pass: the R outputs of one j are contiguous
+        for (int e = threadIdx.x; e < R * J; e += blockDim.x) {
+            const int jj = e / R, c = e % R;
+            const long long j = j0 + jj, k = j & (Ns - 1);
+            dst[(j - k) * R + k + c * Ns] = A[c * JP + jj];
+        }
+    } else {
+        // later passes: for one output digit c the J columns are contiguous
+        for (int e = threadIdx.x; e < R * J; e += blockDim.x) {
+            const int c = e / J, jj = e % J;
+            const long long j = j0 + jj, k = j & (Ns - 1);
+            dst[(j - k) * R + k + c * Ns] = A[c * JP + jj];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
