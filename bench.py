@@ -235,20 +235,25 @@ def run_ours(args):
     side = torch.cuda.Stream() if world > 1 else None
     torch.cuda.synchronize()
     counter = [0]
+    set_free = [None, None]
 
     def step():
         if world == 1:
             eng.process(d0, d1, N_BLOCKS, out=out, inputs_ready=True)    # the recording is resident in HBM
             return
-        acc = accs[counter[0] & 1]
+        which = counter[0] & 1
+        acc = accs[which]
         counter[0] += 1
-        eng.stream.wait_stream(side)                 # this set's previous reduce + clear have finished
+        if set_free[which] is not None:
+            eng.stream.wait_event(set_free[which])   # THIS set's previous reduce + clear have finished
         eng.process(d0, d1, N_BLOCKS, out=out, acc=acc, inputs_ready=True)
         side.wait_stream(eng.stream)
         with torch.cuda.stream(side):
             # the one collective of the path: reduce the small per-integration accumulators to rank 0
             sharding.reduce_accumulators(acc, dst=0)
             acc["flat"].zero_()
+            set_free[which] = torch.cuda.Event()
+            set_free[which].record(side)
 
     def barrier():
         if world > 1:
