@@ -220,6 +220,29 @@ def test_fused_small_nbins_vs_oracle_and_generic(S, N, nb):
     eng.close(); gen.close()
 
 
+@pytest.mark.parametrize("S,N", [(6 * 1024, 1024), (2**15, 2048), (9 * 256, 256)])
+def test_fused_small_nbins_integrate_and_host_pipeline(S, N):
+    """fx_integrate and fx_process_host on the fused kernel below 4096 bins (P mod F != 0 for two shapes)."""
+    nb = 7
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=2, dc0=0.01 - 0.01j, dc1=0.02j, seed=13)
+    eng = FxEngine(S, N, 4, max_blocks=3)
+    assert eng.fused
+    ref = oracle_rows(raw0, raw1, S, N, 2.4e6, 1.4204e9, 0.0, nb)
+    x = eng.process_host(raw0, raw1, nb)                      # 3 chunks of <= 3 blocks
+    for b in range(nb):
+        assert_close(x[b], ref[b], what=f"host pipeline N={N} block {b}")
+    acc = eng.new_accumulators()
+    d0, d1 = dev(raw0), dev(raw1)
+    for b0 in range(0, nb, 3):
+        n = min(3, nb - b0)
+        eng.integrate(d0[2 * S * b0:2 * S * (b0 + n)], d1[2 * S * b0:2 * S * (b0 + n)], acc, n)
+    eng.sync()
+    assert acc["frames"].item() == nb * (S // N)
+    xi, _, _ = FxEngine.finish_integration(acc)
+    assert_close(xi, ref.mean(axis=0), what=f"integrate N={N} vs oracle")
+    eng.close()
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_golden_reference_fixture(golden_dir, tag):
     """Fixtures made by running the reference's own effex.py (tests/golden/make_golden.py)."""
