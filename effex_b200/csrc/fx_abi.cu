@@ -456,15 +456,27 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     if (rc) return rc;
     const int N = h->cfg.nbins;
     if (d_acc_x) {
-        const int n_segs = h->parts_per_block ? (int)o.units : (int)h->h_segs.size();
-        const int G = std::max(1, std::min(64, n_segs / 4));
         if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)N));
-        fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
-            h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
-        FX_LAUNCH_CHECK(h, "integrate_stage1");
+        int G;
+        if (d_xspec) {
+            // rows and accumulators from ONE pass over the partial sums
+            G = (int)std::max<long long>(1, std::min<long long>(64, n_blocks));
+            fx::generic::finalize_integrate_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
+                h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)n_blocks,
+                1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0,
+                d_auto1, h->d_int_scratch);
+            FX_LAUNCH_CHECK(h, "finalize_integrate");
+        } else {
+            const int n_segs = h->parts_per_block ? (int)o.units : (int)h->h_segs.size();
+            G = std::max(1, std::min(64, n_segs / 4));
+            fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
+                h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
+            FX_LAUNCH_CHECK(h, "integrate_stage1");
+        }
         fx::generic::integrate_stage2_kernel<<<(4 * N + 255) / 256, 256, 0, h->stream>>>(
             h->d_int_scratch, N, G, (double)o.units * (double)o.P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
         FX_LAUNCH_CHECK(h, "integrate_stage2");
+        if (d_xspec) return FX_OK;
     }
     if (!d_xspec) return FX_OK;
     dim3 grid((N + 255) / 256, 1);

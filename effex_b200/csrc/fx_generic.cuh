@@ -317,6 +317,46 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__rest
     if (auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
 }
 
+// finalize + integrate in one pass over the partial sums: thread (j, g) walks the blocks of group g,
+// writes each block's row like finalize_rows_kernel and adds the block's un-normalised sums (float64)
+// into scratch[g] in natural bin order -- integrate_stage2_kernel folds the G groups afterwards.
+// grid = (ceil(N/256), G)
+__global__ void __launch_bounds__(256) finalize_integrate_kernel(const float2 *__restrict__ part_x,
+                                                                 const float2 *__restrict__ part_a, int N,
+                                                                 const int *__restrict__ blk_first, int n_blocks,
+                                                                 float inv_frames, const float2 *__restrict__ rot,
+                                                                 float2 *__restrict__ xspec, float *__restrict__ auto0,
+                                                                 float *__restrict__ auto1, double *__restrict__ scratch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int c = (j + (N >> 1)) & (N - 1);
+    const int G = gridDim.y, g = blockIdx.y;
+    const int b0 = (int)((long long)n_blocks * g / G), b1 = (int)((long long)n_blocks * (g + 1) / G);
+    const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);
+    double dxr = 0, dxi = 0, da0 = 0, da1 = 0;
+    for (int b = b0; b < b1; ++b) {
+        const int s0 = blk_first ? blk_first[b] : b;
+        const int s1 = blk_first ? blk_first[b + 1] : b + 1;
+        float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+        for (int s = s0; s < s1; ++s) {
+            const long long o = (long long)s * N + c;
+            const float2 x = part_x[o];
+            const float2 a = part_a[o];
+            xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+        }
+        dxr += xr; dxi += xi; da0 += a0; da1 += a1;
+        xr *= inv_frames; xi *= inv_frames;
+        xspec[(long long)b * N + j] = make_float2(xr * r.x + xi * r.y, xi * r.x - xr * r.y);
+        if (auto0) auto0[(long long)b * N + j] = a0 * inv_frames;
+        if (auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
+    }
+    double *o = scratch + (long long)g * 4 * N;
+    o[2 * c] = dxr;
+    o[2 * c + 1] = dxi;
+    o[2 * N + c] = da0;
+    o[3 * N + c] = da1;
+}
+
 // integrate: float64 accumulators += sum over all segments of the call (natural order, no rot).
 // Two deterministic stages: grid (ceil(N/256), G) partial sums over segment slices into scratch[G][4N],
 // then one pass that folds the G slices into the accumulators.
