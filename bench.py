@@ -216,6 +216,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the FX hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    if world > 1 and not args.no_numa_bind:
+        # host buffers of the e2e leg are allocated below: keep them on the GPU's NUMA node
+        from effex_b200 import hostmem
+        hostmem.bind_to_gpu(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -389,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-blocks", type=int, default=4, help="oracle blocks per worker for cpu_baseline")
     ap.add_argument("--ref-blocks", type=int, default=4, help="oracle blocks per worker per step (--impl reference)")
+    ap.add_argument("--no-numa-bind", dest="no_numa_bind", action="store_true",
+                    help="N>1: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (for runs under ncu; not a bench value)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
