@@ -30,18 +30,18 @@ namespace fx {
 namespace fused4096 {
 
 constexpr int RING_S = 2;
-// exchange planes: 16 tiles of 16 rows x 16 columns, rows padded to 17 elements.  Column-wise and
-// row-wise accesses of a half-warp are both bank-conflict free, and every offset other than the
-// thread's own (row or column) is a compile-time immediate -- no swizzle arithmetic per access.
+// exchange planes: 16 tiles of 16 rows x 16 columns of 16-byte elements (one complex pair-of-channels
+// value per LDS.128/STS.128), rows padded to 17 elements.  Column-wise and row-wise accesses of a
+// quarter-warp are both bank-conflict free, and every offset other than the thread's own (row or column)
+// is a compile-time immediate -- no swizzle arithmetic per access.
 constexpr int ROWP = 17;
 constexpr int TILE = 16 * ROWP;
 constexpr int NP = 16 * TILE;
 
 struct __align__(16) SmemS {
-    float2 Xr[2][NP];            // 2 x 34 KB exchange planes (re ch0, re ch1), double buffered
-    float2 Xi[2][NP];            // 2 x 34 KB exchange planes (im ch0, im ch1)
-    float4 twA[8][NT];           // row 2g+h: (W4096^(t*k1), W4096^(t*(k1+4))) for k1 = g + 8h  (one LDS.128 per pair)
-    float4 twB[8][16];           // row 2g+h: (W256^(n3*k2), W256^(n3*(k2+4))) for k2 = g + 8h
+    float4 X[2][NP];             // 2 x 68 KB exchange planes of (re ch0, re ch1, im ch0, im ch1), double buffered
+    float4 twA[8][NT];           // row 2g+h: stage-A twiddles of registers 4g+2h and 4g+2h+1 (one LDS.128 per pair)
+    float4 twB[8][16];           // row 2g+h: W256^(n3*k2) of registers 4g+2h and 4g+2h+1, k2 = perm16(register)
     unsigned short raw[RING_S][2][N];
     unsigned long long mbar[RING_S + 1];
     uint32_t tmem_base;
@@ -77,6 +77,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float4 &p, float4 &q) {
 // shared-memory store of one packed pair, spelled as two 32-bit registers: with a plain `*p = v` ptxas
 // (12.9) copies every 64-bit FFMA2 result into one staging pair before its STS.64 (2 MOV per store,
 // serialised on that pair's scoreboard) -- 32 stores per exchange, 6% of the kernel's time
+__device__ __forceinline__ void sts_c2(float4 *p, const C2 &z) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(z.r.x),
+                 "f"(z.r.y), "f"(z.i.x), "f"(z.i.y)
+                 : "memory");
+}
+__device__ __forceinline__ C2 lds_c2(const float4 *p) {
+    const float4 q = *p;
+    return {f2(q.x, q.y), f2(q.z, q.w)};
+}
 __device__ __forceinline__ void sts_pair(float2 *p, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -337,7 +346,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
 #pragma unroll
                     for (int f = 0; f < F; ++f) dft_small<RP>(&v[f * RP]);
                 }
-                float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
+                float4 *xx = sm.X[buf];
                 float4 tq[2], tqn[2];
                 tq[0] = sm.twA[0][t];
                 tq[1] = sm.twA[1][t];
@@ -353,8 +362,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
                         C2 z = v[4 * g + b];
                         const float4 q = tq[b >> 1];
                         if (row % RP != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
-                        sts_pair(&xr[row * TILE + k1B * ROWP + lo], z.r);
-                        sts_pair(&xi[row * TILE + k1B * ROWP + lo], z.i);
+                        sts_c2(&xx[row * TILE + k1B * ROWP + lo], z);
                     }
                     tq[0] = tqn[0];
                     tq[1] = tqn[1];
@@ -364,9 +372,9 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
 
         // ---- stages B, C and the X-engine of the frame held in exchange buffer `buf` ---------------
         auto fft_rest = [&](int buf, int nv) {
-            float2 *xr = sm.Xr[buf], *xi = sm.Xi[buf];
+            float4 *xx = sm.X[buf];
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = {xr[k1B * TILE + n2 * ROWP + lo], xi[k1B * TILE + n2 * ROWP + lo]};
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds_c2(&xx[k1B * TILE + n2 * ROWP + lo]);
             dft16(v);
             __syncwarp();
             {
@@ -385,8 +393,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
                         C2 z = v[4 * g + b];
                         const float4 q = tq[b >> 1];
                         if (k2 != 0) z = (b & 1) ? cmuls(z, q.z, q.w) : cmuls(z, q.x, q.y);
-                        sts_pair(&xr[k1B * TILE + k2 * ROWP + lo], z.r);
-                        sts_pair(&xi[k1B * TILE + k2 * ROWP + lo], z.i);
+                        sts_c2(&xx[k1B * TILE + k2 * ROWP + lo], z);
                     }
                     tq[0] = tqn[0];
                     tq[1] = tqn[1];
@@ -394,7 +401,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
             }
             __syncwarp();
 #pragma unroll
-            for (int n3 = 0; n3 < 16; ++n3) v[n3] = {xr[k1B * TILE + lo * ROWP + n3], xi[k1B * TILE + lo * ROWP + n3]};
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = lds_c2(&xx[k1B * TILE + lo * ROWP + n3]);
             dft16(v);
             if (LOGF == 0 || fslot < nv) {        // frame slots beyond a block's last frame hold no data
 #pragma unroll
@@ -428,7 +435,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
 
         // ---- segment epilogue (both exchange buffers are free after the last barrier) ----------------
         {
-            float2 *xs = &sm.Xr[0][0];                          // cross in xs[0..N), autos in xs[N..2N)
+            float2 *xs = reinterpret_cast<float2 *>(&sm.X[0][0]);   // cross in xs[0..N), autos in xs[N..2N)
             // staging index = frame slot * NL + bin; bin = k1' + RP*(k2 + 16*k3) with k2 = lo, k3 = perm16(jj)
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {

@@ -19,3 +19,18 @@ def test_reader_delivers_whole_blocks_in_order(tmp_path):
     np.testing.assert_array_equal(np.concatenate(got0), a[2 * S:2 * S * nb])
     np.testing.assert_array_equal(np.concatenate(got1), b[2 * S:2 * S * nb])
     assert RecordingReader(str(p0), str(p1), S, batch_blocks=4, max_blocks=3).n_blocks == 3
+
+
+def test_hostmem_bind_is_safe_without_nvml_or_gpu():
+    """bind_to_gpu never widens the affinity mask and is a no-op when NVML has no answer."""
+    import os
+    from effex_b200 import hostmem
+    if not hasattr(os, "sched_getaffinity"):
+        return
+    before = os.sched_getaffinity(0)
+    cpus = hostmem.bind_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    try:
+        assert after <= before and set(cpus) == after
+    finally:
+        os.sched_setaffinity(0, before)
