@@ -328,7 +328,7 @@ int stockham_passes(fx_handle *h, float2 *buf, float2 *tmp, long long M, long lo
     for (int p = 0; p < npass; ++p) {
         const int bits = logM / npass + (p < logM % npass ? 1 : 0);
         const long long R = 1ll << bits;
-        const size_t smem = (2 * (size_t)R * (fx::generic::kPassJ + 1) + (size_t)R / 2) * sizeof(float2);
+        const size_t smem = (2 * (size_t)R * (fx::generic::kPassJ + 1) + (size_t)R) * sizeof(float2);
         const int threads = (int)std::min<long long>(512, R * fx::generic::kPassJ / 2);
         for (long long r0 = 0; r0 < rows; r0 += 65535) {
             const long long nr = std::min<long long>(65535, rows - r0);
@@ -376,21 +376,37 @@ int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, i
     return timed ? end_timed(h, ep) : FX_OK;
 }
 
+// PFB FIR of `nb` units of one channel into w[nb][P][N]: the 4-tap kernel for the reference's ntaps,
+// the general one otherwise
+template <bool U8>
+int launch_fir(fx_handle *h, const void *in, long long S, int P, long long nb, const float *taps,
+               const unsigned long long *sums, float2 *w, const void *halo, long long mean_count) {
+    const int N = h->cfg.nbins, T = h->cfg.ntaps;
+    if (T == 4) {
+        dim3 grid((N + 255) / 256, (P + fx::generic::kFir4Frames - 1) / fx::generic::kFir4Frames, (unsigned)nb);
+        fx::generic::pfb_fir4_kernel<U8><<<grid, 256, 0, h->stream>>>(in, S, N, P, taps, sums, 4, h->cfg.dc_remove, w, halo,
+                                                                     mean_count);
+    } else {
+        dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, (unsigned)nb);
+        fx::generic::pfb_fir_kernel<U8><<<grid, 256, 0, h->stream>>>(in, S, N, T, P, taps, sums, 4, h->cfg.dc_remove, w,
+                                                                    halo, mean_count);
+    }
+    FX_LAUNCH_CHECK(h, "pfb_fir");
+    return FX_OK;
+}
+
 // generic path for a chunk of units: FIR -> FFT -> X-engine into parts[b0 .. b0+nb)
 int run_generic_chunk(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long b0, long long nb,
                       const PassOpts &o) {
     const int N = h->cfg.nbins, T = h->cfg.ntaps, P = (int)o.P;
     const long long S = o.S;
-    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, (unsigned)nb);
-    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq0 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
-                                                                  h->d_sums + 4 * b0, 4, h->cfg.dc_remove, h->d_g0,
-                                                                  b0 == 0 ? o.halo0 : nullptr, o.mean_count);
-    FX_LAUNCH_CHECK(h, "pfb_fir");
-    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq1 + 2 * S * b0, S, N, T, P, h->d_taps_u8,
-                                                                  h->d_sums + 4 * b0 + 2, 4, h->cfg.dc_remove, h->d_g1,
-                                                                  b0 == 0 ? o.halo1 : nullptr, o.mean_count);
-    FX_LAUNCH_CHECK(h, "pfb_fir");
-    int rc = fft_batched(h, h->d_g0, h->d_gtmp, N, nb * P, 0, 0, true);
+    int rc = launch_fir<true>(h, d_iq0 + 2 * S * b0, S, P, nb, h->d_taps_u8, h->d_sums + 4 * b0, h->d_g0,
+                              b0 == 0 ? o.halo0 : nullptr, o.mean_count);
+    if (rc) return rc;
+    rc = launch_fir<true>(h, d_iq1 + 2 * S * b0, S, P, nb, h->d_taps_u8, h->d_sums + 4 * b0 + 2, h->d_g1,
+                          b0 == 0 ? o.halo1 : nullptr, o.mean_count);
+    if (rc) return rc;
+    rc = fft_batched(h, h->d_g0, h->d_gtmp, N, nb * P, 0, 0, true);
     if (rc) return rc;
     rc = fft_batched(h, h->d_g1, h->d_gtmp, N, nb * P, 0, 0, true);
     if (rc) return rc;
@@ -642,7 +658,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      2 * 4096 * (int)sizeof(float2)));
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::stockham_radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (2 * 256 * (fx::generic::kPassJ + 1) + 128) * (int)sizeof(float2)));
+                                     (2 * 256 * (fx::generic::kPassJ + 1) + 256) * (int)sizeof(float2)));
     if (h->fused) {
         CREATE_CUDA(cudaMalloc(&h->d_taps4, fx::fused4096::N * sizeof(float4)));
         CREATE_CUDA(cudaMalloc(&h->d_twA, 16 * 256 * sizeof(float2)));
@@ -914,11 +930,9 @@ int fx_pfb_c64(fx_handle *h, const float *d_x, float *d_frames) {
     const int N = h->cfg.nbins, T = h->cfg.ntaps, P = h->P;
     int rc = ensure_generic(h, (size_t)P * N);
     if (rc) return rc;
-    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);
-    fx::generic::pfb_fir_kernel<false><<<grid, 256, 0, h->stream>>>(d_x, h->cfg.num_samp, N, T, P, h->d_taps_c,
-                                                                   nullptr, 0, 0, out);
-    FX_LAUNCH_CHECK(h, "pfb_fir");
+    rc = launch_fir<false>(h, d_x, h->cfg.num_samp, P, 1, h->d_taps_c, nullptr, out, nullptr, 0);
+    if (rc) return rc;
     return fft_batched(h, out, h->d_gtmp, N, P, 0, 1, true);
 }
 
@@ -932,11 +946,9 @@ int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames) {
     if (rc) return rc;
     rc = launch_sums(h, d_iq, d_iq, 1);
     if (rc) return rc;
-    dim3 grid((N + 255) / 256, (P + fx::generic::kFirFrames - 1) / fx::generic::kFirFrames, 1);
     float2 *out = reinterpret_cast<float2 *>(d_frames);
-    fx::generic::pfb_fir_kernel<true><<<grid, 256, 0, h->stream>>>(d_iq, h->cfg.num_samp, N, T, P, h->d_taps_u8,
-                                                                  h->d_sums, 4, h->cfg.dc_remove, out);
-    FX_LAUNCH_CHECK(h, "pfb_fir");
+    rc = launch_fir<true>(h, d_iq, h->cfg.num_samp, P, 1, h->d_taps_u8, h->d_sums, out, nullptr, 0);
+    if (rc) return rc;
     rc = release_sums(h);
     if (rc) return rc;
     return fft_batched(h, out, h->d_gtmp, N, P, 0, 1, true);

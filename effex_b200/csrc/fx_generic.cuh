@@ -139,6 +139,60 @@ __global__ void __launch_bounds__(256) pfb_fir_kernel(const void *__restrict__ i
     }
 }
 
+// T = 4 (the reference's ntaps, effex.py:115): a thread walks kFir4Frames consecutive frames of one
+// branch with the three previous samples in registers -- one load and 8 FMAs per output.
+// grid = (ceil(N/256), ceil(P/kFir4Frames), n_blocks)
+constexpr int kFir4Frames = 32;
+template <bool U8>
+__global__ void __launch_bounds__(256) pfb_fir4_kernel(const void *__restrict__ in, long long S, int N, int P,
+                                                       const float *__restrict__ taps,
+                                                       const unsigned long long *__restrict__ sums, int sum_stride,
+                                                       int dc_remove, float2 *__restrict__ w,
+                                                       const void *__restrict__ halo = nullptr, long long mean_count = 0) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.y * kFir4Frames, b = blockIdx.z;
+    __shared__ float s_mean[2];
+    if (U8 && threadIdx.x == 0) {
+        if (dc_remove) {
+            const double den = (double)(mean_count > 0 ? mean_count : S);
+            s_mean[0] = (float)((double)sums[(long long)b * sum_stride] / den);
+            s_mean[1] = (float)((double)sums[(long long)b * sum_stride + 1] / den);
+        } else {
+            s_mean[0] = s_mean[1] = 127.5f;
+        }
+    }
+    if (U8) __syncthreads();
+    if (p >= N) return;
+    const float mi = U8 ? s_mean[0] : 0.f, mq = U8 ? s_mean[1] : 0.f;
+    const bool have_halo = halo && b == 0;
+    // sample of frame i (block-relative; i < 0 reads the halo or is zero history)
+    auto sample = [&](int i) -> float2 {
+        const void *src = in;
+        long long s = (long long)b * S + (long long)i * N + p;
+        if (i < 0) {
+            if (!have_halo) return make_float2(0.f, 0.f);
+            src = halo;
+            s = (long long)(i + 3) * N + p;
+        }
+        if (U8) {
+            const uchar2 q = reinterpret_cast<const uchar2 *>(src)[s];
+            return make_float2((float)q.x - mi, (float)q.y - mq);
+        }
+        return reinterpret_cast<const float2 *>(src)[s];
+    };
+    const float t0 = taps[p], t1 = taps[(long long)N + p], t2 = taps[2ll * N + p], t3 = taps[3ll * N + p];
+    float2 x1 = sample(i0 - 1), x2 = sample(i0 - 2), x3 = sample(i0 - 3);
+    const int i1 = min(i0 + kFir4Frames, P);
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+        const float2 x0 = sample(i);
+        w[((long long)b * P + i) * N + p] =
+            make_float2(fmaf(t0, x0.x, fmaf(t1, x1.x, fmaf(t2, x2.x, t3 * x3.x))),
+                        fmaf(t0, x0.y, fmaf(t1, x1.y, fmaf(t2, x2.y, t3 * x3.y))));
+        x3 = x2; x2 = x1; x1 = x0;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Batched forward/inverse FFT of length N = 2^logN <= 4096, one row per CTA,
 // radix-2 Stockham autosort in shared memory.  phase_post: multiply bin c by
@@ -190,7 +244,7 @@ __global__ void __launch_bounds__(512) fft_rows_kernel(const float2 *__restrict_
 // R-point transforms of its J columns as radix-2 autosort stages in shared memory, and stores.  A
 // transform of 2^16 points is 2 passes over HBM, of 2^19 points 3 (a radix-2 pass per stage was 16 / 19).
 // Used for transforms that do not fit one CTA: the 2n-point lag-search FFTs and N > 4096 channelizers.
-// grid = (M/R/J, batch), dynamic smem = (2*R*(J+1) + R/2)*sizeof(float2)
+// grid = (M/R/J, batch), dynamic smem = (2*R*(J+1) + R)*sizeof(float2)
 constexpr int kPassJ = 16;
 __global__ void __launch_bounds__(512) stockham_radix_pass_kernel(const float2 *__restrict__ in,
                                                                   float2 *__restrict__ out, long long M,
@@ -218,28 +272,51 @@ __global__ void __launch_bounds__(512) stockham_radix_pass_kernel(const float2 *
         }
         A[r * JP + jj] = v;
     }
-    // W_R^i, i < R/2, once per CTA: stage s uses W_(2 ns)^kk = W_R^(kk * R/(2 ns))
+    // W_R^i, i < R, once per CTA: a radix-4 stage with sub-length ns uses W_(4 ns)^(q k) = W_R^(q k R/(4 ns))
     float2 *tw = B + R * JP;
-    const int half = R >> 1;
-    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
         float sn, cs;
-        sincospif(sgn * (float)i / (float)half, &sn, &cs);
+        sincospif(sgn * 2.f * (float)i / (float)R, &sn, &cs);
         tw[i] = make_float2(cs, sn);
     }
     __syncthreads();
-    for (int s = 0; s < logR; ++s) {
-        const int ns = 1 << s;
+    int ns = 1;
+    if (logR & 1) {
+        // one radix-2 stage (ns = 1: no twiddles)
+        const int half = R >> 1;
         for (int e = threadIdx.x; e < half * J; e += blockDim.x) {
             const int b = e / J, jj = e % J;
-            const int kk = b & (ns - 1);
-            const float2 wv = tw[kk << (logR - 1 - s)];
-            const float cs = wv.x, sn = wv.y;
-            const float2 v0 = A[b * JP + jj];
-            const float2 a = A[(b + half) * JP + jj];
-            const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
-            const int o = ((b - kk) << 1) + kk;
-            B[o * JP + jj] = make_float2(v0.x + v1.x, v0.y + v1.y);
-            B[(o + ns) * JP + jj] = make_float2(v0.x - v1.x, v0.y - v1.y);
+            const float2 v0 = A[b * JP + jj], v1 = A[(b + half) * JP + jj];
+            B[(2 * b) * JP + jj] = make_float2(v0.x + v1.x, v0.y + v1.y);
+            B[(2 * b + 1) * JP + jj] = make_float2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        float2 *t = A; A = B; B = t;
+        ns = 2;
+    }
+    const int quarter = R >> 2;
+    for (; ns < R; ns <<= 2) {
+        const int step = R / (4 * ns);
+        for (int e = threadIdx.x; e < quarter * J; e += blockDim.x) {
+            const int b = e / J, jj = e % J;
+            const int k = b & (ns - 1);
+            const float2 a0 = A[b * JP + jj];
+            float2 a1 = A[(b + quarter) * JP + jj], a2 = A[(b + 2 * quarter) * JP + jj], a3 = A[(b + 3 * quarter) * JP + jj];
+            if (k) {
+                const float2 w1 = tw[k * step], w2 = tw[2 * k * step], w3 = tw[3 * k * step];
+                a1 = make_float2(a1.x * w1.x - a1.y * w1.y, a1.x * w1.y + a1.y * w1.x);
+                a2 = make_float2(a2.x * w2.x - a2.y * w2.y, a2.x * w2.y + a2.y * w2.x);
+                a3 = make_float2(a3.x * w3.x - a3.y * w3.y, a3.x * w3.y + a3.y * w3.x);
+            }
+            const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+            const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+            // forward: W4 = -i; inverse: +i   (sgn = -1 forward)
+            const float2 rot = make_float2(-sgn * d13.y, sgn * d13.x);      // sgn*i*d13
+            const int o = ((b - k) << 2) + k;
+            B[o * JP + jj] = make_float2(s02.x + s13.x, s02.y + s13.y);
+            B[(o + ns) * JP + jj] = make_float2(d02.x + rot.x, d02.y + rot.y);
+            B[(o + 2 * ns) * JP + jj] = make_float2(s02.x - s13.x, s02.y - s13.y);
+            B[(o + 3 * ns) * JP + jj] = make_float2(d02.x - rot.x, d02.y - rot.y);
         }
         __syncthreads();
         float2 *t = A; A = B; B = t;
