@@ -21,4 +21,12 @@ for S, N, nb in [(3 * 4096, 4096, 3), (5 * 2048, 2048, 3), (7 * 1024, 1024, 3), 
     print(f"S={S} N={N} fused={eng.fused} rel err {err:.2e}")
     eng.close()
 assert worst < 1e-4
+# lag search: forward + inverse radix passes at 2n = 2^14, accumulated over 2 blocks
+S = 2**13
+raw0, raw1 = synth.correlated_pair(2 * S, delay=5, seed=4)
+eng = FxEngine(S, 1024, 4, max_blocks=2)
+n, imax, *_ = eng.lag(torch.from_numpy(raw0).cuda(), torch.from_numpy(raw1).cuda(), 2)
+assert n - imax == 5, (n, imax)
+print("lag ok:", n - imax)
+eng.close()
 print("sanitize_small ok, worst rel err %.2e" % worst)
