@@ -12,6 +12,7 @@
 #include "fx_fused4096.cuh"
 #include "fx_fused4096s.cuh"
 #include "fx_generic.cuh"
+#include "fx_bigfft.cuh"
 
 namespace {
 
@@ -29,6 +30,11 @@ struct fx_handle {
     int logN = 0;
     int num_sms = 148;
     bool fused = false;
+    bool planning_big = false; // plan_segments is being called for virtual blocks of the big path
+    bool big = false;          // nbins = 2^logG * 4096, ntaps = 4: head + tail kernels (fx_bigfft.cuh)
+    int logG = 0;
+    float4 *d_z = nullptr;     // big path: Z[blocks of a chunk][P][G][4096]
+    size_t z_cap = 0;          // in float4 elements
     int logF = 0;     // fused kernel: frames per 4096-sample super-frame = 2^logF (nbins = 4096 >> logF)
     bool staggered = false;   // fused path uses fused_kernel_stag
     bool taps_set = false;
@@ -51,7 +57,7 @@ struct fx_handle {
     bool sums_free_recorded[2] = {false, false};
     int sums_idx = 0;
     float2 *d_part_x = nullptr, *d_part_a = nullptr;
-    size_t part_cap = 0;                      // in segments
+    size_t part_cap = 0;                      // in float2 elements per buffer
     int *d_plan = nullptr;                     // [segments x4 | cta_first | blk_first]
     size_t segs_cap = 0, off_cta = 0, off_blk = 0;
     std::vector<fx::fused4096::Segment> h_segs;
@@ -169,16 +175,16 @@ int release_sums(fx_handle *h) {
     return FX_OK;
 }
 
-int ensure_parts(fx_handle *h, size_t n_segs) {
-    if (n_segs <= h->part_cap) return FX_OK;
+int ensure_parts(fx_handle *h, size_t n_segs, size_t bins_per_seg = 0) {
+    const size_t elems = n_segs * (bins_per_seg ? bins_per_seg : (size_t)h->cfg.nbins);
+    if (elems <= h->part_cap) return FX_OK;
     if (h->d_part_x) cudaFree(h->d_part_x);
     if (h->d_part_a) cudaFree(h->d_part_a);
     h->d_part_x = h->d_part_a = nullptr;
     h->part_cap = 0;
-    const size_t bytes = n_segs * (size_t)h->cfg.nbins * sizeof(float2);
-    FX_CUDA(h, cudaMalloc(&h->d_part_x, bytes));
-    FX_CUDA(h, cudaMalloc(&h->d_part_a, bytes));
-    h->part_cap = n_segs;
+    FX_CUDA(h, cudaMalloc(&h->d_part_x, elems * sizeof(float2)));
+    FX_CUDA(h, cudaMalloc(&h->d_part_a, elems * sizeof(float2)));
+    h->part_cap = elems;
     return FX_OK;
 }
 
@@ -234,7 +240,7 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
     FX_CUDA(h, cudaMemcpy(h->d_plan, flat.data(), n_int * sizeof(int), cudaMemcpyHostToDevice));
     h->planned_blocks = n_blocks;
     h->planned_P = planned_P;
-    return ensure_parts(h, h->h_segs.size());
+    return ensure_parts(h, h->h_segs.size(), h->planning_big ? (size_t)fx::fused4096::N : 0);
 }
 
 // Options of one pass: reference semantics (independent blocks) or one streaming span.
@@ -294,6 +300,61 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     rc = release_sums(h);
     if (rc) return rc;
     return end_timed(h, ep);
+}
+
+// nbins = G*4096: head kernel -> Z -> tail kernel -> rows, a chunk of blocks at a time (Z <= 1 GiB)
+int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
+            float *d_auto0, float *d_auto1) {
+    using namespace fx::bigfft;
+    const int NB = h->cfg.nbins, G = 1 << h->logG, P = h->P;
+    const long long S = h->cfg.num_samp;
+    int rc = launch_sums(h, d_iq0, d_iq1, n_blocks, S);
+    if (rc) return rc;
+    const size_t per_block = (size_t)P * NB;                              // float4 elements of Z
+    long long chunk = (long long)std::max<size_t>(1, (size_t(1) << 26) / per_block);
+    chunk = std::min<long long>(std::min<long long>(chunk, n_blocks), 65535 / G);
+    if (chunk * per_block > h->z_cap) {
+        if (h->d_z) cudaFree(h->d_z);
+        h->d_z = nullptr;
+        h->z_cap = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_z, chunk * per_block * sizeof(float4)));
+        h->z_cap = chunk * per_block;
+    }
+    for (long long b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const long long nb = std::min(chunk, n_blocks - b0);
+        const uint8_t *c0 = d_iq0 + 2 * S * b0, *c1 = d_iq1 + 2 * S * b0;
+        const unsigned long long *su = h->d_sums + 4 * b0;
+        dim3 hg(fx::fused4096::N / 256, (unsigned)P, (unsigned)nb);
+        switch (h->logG) {
+            case 1: head_kernel<1><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 2: head_kernel<2><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 3: head_kernel<3><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            default: head_kernel<4><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+        }
+        FX_LAUNCH_CHECK(h, "bigfft_head");
+        h->planning_big = true;
+        rc = plan_segments(h, nb * G, P);                                 // virtual blocks (block, k1)
+        h->planning_big = false;
+        if (rc) return rc;
+        TailParams prm;
+        prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
+        prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
+        prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = P;
+        EventPair ep{};
+        rc = begin_timed(h, ep);
+        if (rc) return rc;
+        tail_kernel<<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
+        FX_LAUNCH_CHECK(h, "bigfft_tail");
+        rc = end_timed(h, ep);
+        if (rc) return rc;
+        dim3 fg((NB + 255) / 256, (unsigned)nb);
+        finalize_kernel<<<fg, 256, 0, h->stream>>>(h->d_part_x, h->d_part_a, NB, h->logG, h->d_plan + h->off_blk,
+                                                   1.0f / (float)P, h->rot_set ? h->d_rot : nullptr,
+                                                   reinterpret_cast<float2 *>(d_xspec) + b0 * NB,
+                                                   d_auto0 ? d_auto0 + b0 * NB : nullptr, d_auto1 ? d_auto1 + b0 * NB : nullptr);
+        FX_LAUNCH_CHECK(h, "bigfft_finalize");
+    }
+    return release_sums(h);
 }
 
 int ensure_generic(fx_handle *h, size_t elems) {
@@ -467,6 +528,8 @@ PassOpts block_opts(const fx_handle *h, long long n_blocks) {
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
                    float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
                    double *d_acc_a1 = nullptr, double *d_frames = nullptr, const PassOpts *span = nullptr) {
+    if (h->big && !span && d_xspec && !d_acc_x && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
+        return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1);
     const PassOpts o = span ? *span : block_opts(h, n_blocks);
     int rc = run_parts(h, d_iq0, d_iq1, o);
     if (rc) return rc;
@@ -632,6 +695,9 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     h->fused = cfg->nbins >= 256 && cfg->nbins <= fx::fused4096::N && cfg->ntaps == fx::fused4096::T &&
                (cfg->num_samp % 8) == 0 && !(cfg->flags & FX_FLAG_FORCE_GENERIC);
     h->logF = h->fused ? 12 - h->logN : 0;
+    h->big = cfg->nbins > fx::fused4096::N && cfg->nbins <= 65536 && cfg->ntaps == fx::fused4096::T &&
+             !(cfg->flags & FX_FLAG_FORCE_GENERIC);
+    h->logG = h->big ? h->logN - 12 : 0;
     auto bail = [&](const std::string &m) { g_create_error = m; fx_destroy(h); return FX_ERR_CUDA; };
 #define CREATE_CUDA(expr)                                                        \
     do {                                                                         \
@@ -659,7 +725,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                      2 * 4096 * (int)sizeof(float2)));
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::stockham_radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * 256 * (fx::generic::kPassJ + 1) + 256) * (int)sizeof(float2)));
-    if (h->fused) {
+    if (h->fused || h->big) {
         CREATE_CUDA(cudaMalloc(&h->d_taps4, fx::fused4096::N * sizeof(float4)));
         CREATE_CUDA(cudaMalloc(&h->d_twA, 16 * 256 * sizeof(float2)));
         CREATE_CUDA(cudaMalloc(&h->d_twB, 16 * 16 * sizeof(float2)));
@@ -682,7 +748,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         // register j holds k2 = perm16(j) and carries W256^(n3*k2).
         std::vector<float4> twAp(8 * 256), twBp(8 * 16);
         {
-            const int RP = 16 >> h->logF, NL = cfg->nbins;
+            const int RP = 16 >> h->logF, NL = fx::fused4096::N >> h->logF;
             auto wA = [&](int j, int t) {
                 const int k1p = fx::fused4096::row_of(h->logF, j) % RP;
                 const double a = -2.0 * M_PI * (double)((k1p * t) % NL) / (double)NL;
@@ -713,6 +779,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                  (const void *)fused_kernel_stag<4>};
             CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         }
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(fx::bigfft::SmemT)));
         // the lock-step cross-check kernel exists for 4096 bins only
         h->staggered = !(cfg->flags & FX_FLAG_LOCKSTEP_KERNEL) || h->logF != 0;
     }
@@ -729,7 +797,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

@@ -1,0 +1,274 @@
+// fx_bigfft.cuh -- nbins = G * 4096 (8192 .. 65536), ntaps = 4: two kernels around ONE intermediate.
+//
+// FIR state for more than 4096 positions does not fit tensor memory, and a frame does not fit shared
+// memory, so the N-point transform is split once, decimation in frequency (n = n1*4096 + n2, n1 < G):
+//
+//   X[k1 + G*k2] = sum_n2 W4096^(n2*k2) * [ W_N^(n2*k1) * sum_n1 w[n1*4096 + n2] * W_G^(n1*k1) ]
+//
+//   head_kernel   unpack + DC removal + 4-tap direct-form FIR for the G samples {n1*4096 + n2} of a thread,
+//                 G-point DFT in registers, twiddle W_N^(n2*k1)  ->  Z[block][frame][k1][n2]  (16 B: both
+//                 channels, re/im), written once, read once
+//   tail_kernel   the fused kernel's stages A, B, C and X-engine (fx_fused4096s.cuh: staggered warp
+//                 groups, padded exchange tiles, packed FP32) with stage A fed from Z instead of the FIR;
+//                 a "virtual block" is (block, k1): its 4096 accumulated bins are k1 + G*k2
+//
+// HBM traffic per pair-sample: 4 B raw (re-read through L2 by the four taps) + 16 B Z out + 16 B Z in,
+// against ~100 B for the unfused kernels (FIR out, two FFT passes in and out, X-engine in).
+// Replaces the same reference lines as the fused kernel (effex.py:394-395, :508-509, :520-521, :553).
+#pragma once
+#include "fx_fused4096s.cuh"
+
+namespace fx {
+namespace bigfft {
+
+using fused4096::N;        // 4096: length of the transforms the tail kernel runs
+using fused4096::NT;
+using fused4096::NP;
+using fused4096::ROWP;
+using fused4096::Segment;
+using fused4096::TILE;
+
+// ---- head ------------------------------------------------------------------------------------------
+// grid = (4096/256, P, n_blocks), 256 threads; thread = one n2, all G values of n1
+template <int LOGG>
+__global__ void __launch_bounds__(256) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
+                                                   long long S, int P, const float *__restrict__ taps,
+                                                   const unsigned long long *__restrict__ sums, int dc_remove,
+                                                   float4 *__restrict__ z) {
+    constexpr int G = 1 << LOGG;
+    constexpr int NB = N << LOGG;                  // nbins
+    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y, b = blockIdx.z;
+    __shared__ float s_mean[4];                    // byte means: ch0 I, ch0 Q, ch1 I, ch1 Q
+    if (threadIdx.x < 4) {
+        s_mean[threadIdx.x] = dc_remove ? (float)((double)sums[4ll * b + threadIdx.x] / (double)S) : 127.5f;
+    }
+    __syncthreads();
+    const float2 mI = f2(s_mean[0], s_mean[2]), mQ = f2(s_mean[1], s_mean[3]);
+    const uchar2 *x0 = reinterpret_cast<const uchar2 *>(iq0) + (long long)b * S;
+    const uchar2 *x1 = reinterpret_cast<const uchar2 *>(iq1) + (long long)b * S;
+    C2 v[G];
+    const int kmax = i < 3 ? i : 3;                // zero history before frame 0 of the block
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int n = g * N + n2;
+        float2 ar = f2(0.f, 0.f), ai = f2(0.f, 0.f);
+        for (int k = 0; k <= kmax; ++k) {
+            const long long s = (long long)(i - k) * NB + n;
+            const uchar2 a = x0[s], c = x1[s];
+            const float h = taps[(long long)k * NB + n];
+            ar = f2fmas(f2sub(f2((float)a.x, (float)c.x), mI), h, ar);
+            ai = f2fmas(f2sub(f2((float)a.y, (float)c.y), mQ), h, ai);
+        }
+        v[g] = {ar, ai};
+    }
+    if constexpr (G == 16) {
+        C2(&v16)[16] = reinterpret_cast<C2(&)[16]>(v);
+        dft16(v16);
+    } else {
+        fused4096::dft_small<G>(v);
+    }
+    float4 *zf = z + ((long long)b * P + i) * (long long)NB + n2;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const int k1 = fused4096::perm_rp(G, j);
+        C2 y = v[j];
+        if (k1 != 0) {
+            float sn, cs;
+            sincospif(-2.f * (float)((n2 * k1) & (NB - 1)) / (float)NB, &sn, &cs);     // exact argument
+            y = cmuls(y, cs, sn);
+        }
+        zf[(long long)k1 * N] = make_float4(y.r.x, y.r.y, y.i.x, y.i.y);
+    }
+}
+
+// ---- tail ------------------------------------------------------------------------------------------
+struct __align__(16) SmemT {
+    float4 X[2][NP];             // exchange planes, as in the fused kernel
+    float4 twA[8][NT];
+    float4 twB[8][16];
+    unsigned long long mbar;
+};
+
+struct TailParams {
+    const float4 *z;             // [n_blocks][P][G][4096]
+    const float4 *twAp, *twBp;   // the fused kernel's tables for 4096 bins
+    const Segment *segs;         // segments over virtual blocks vb = block * G + k1
+    const int *cta_first;
+    float2 *part_x, *part_a;     // [n_segs][4096]
+    int G, P;
+};
+
+__global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
+    using namespace fused4096;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemT &sm = *reinterpret_cast<SmemT *>(smem_raw);
+    const int t = threadIdx.x;
+    const int grp = __shfl_sync(0xffffffffu, t >> 7, 0);     // 0: stage A first, 1: stages B, C first
+    if (t == 0) {
+        mbar_init(&sm.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.mbar, (uint32_t)(sizeof(sm.twA) + sizeof(sm.twB)));
+        tma_load_1d(&sm.twA[0][0], prm.twAp, (uint32_t)sizeof(sm.twA), &sm.mbar);
+        tma_load_1d(&sm.twB[0][0], prm.twBp, (uint32_t)sizeof(sm.twB), &sm.mbar);
+    }
+    __syncthreads();
+    mbar_wait(&sm.mbar, 0);
+    const int k1B = t >> 4, lo = t & 15;
+    const long long fstride = (long long)prm.G * N;            // float4 elements between frames of one k1
+
+    const int seg_end = prm.cta_first[blockIdx.x + 1];
+    for (int seg = prm.cta_first[blockIdx.x]; seg < seg_end; ++seg) {
+        const Segment sg = prm.segs[seg];
+        const int blk = sg.block / prm.G, k1 = sg.block % prm.G;
+        const float4 *zseg = prm.z + (((long long)blk * prm.P + sg.f0) * prm.G + k1) * N;
+        float2 accx[16], acca[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            accx[j] = f2(0.f, 0.f);
+            acca[j] = f2(0.f, 0.f);
+        }
+        C2 v[16];
+
+        // stage A of frame j of the segment: 16 values of Z -> DFT16 -> twiddle -> exchange plane `buf`
+        auto stage_a = [&](int j, int buf) {
+            const float4 *zf = zseg + (long long)j * fstride;
+            if (t == 0 && j + 1 < sg.nf)       // pull the next frame (64 KB) into L2 while this one is transformed
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(zf + fstride), "r"(N * 16) : "memory");
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const float4 q = __ldcs(zf + t + NT * r);      // read once: streaming
+                v[r] = {f2(q.x, q.y), f2(q.z, q.w)};
+            }
+            dft16(v);
+            float4 *xx = sm.X[buf];
+            float4 tq[2], tqn[2];
+            tq[0] = sm.twA[0][t];
+            tq[1] = sm.twA[1][t];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g < 3) {
+                    tqn[0] = sm.twA[2 * g + 2][t];
+                    tqn[1] = sm.twA[2 * g + 3][t];
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int row = g + 4 * b;                 // = perm16(4g + b)
+                    C2 zv = v[4 * g + b];
+                    const float4 q = tq[b >> 1];
+                    if (row != 0) zv = (b & 1) ? cmuls(zv, q.z, q.w) : cmuls(zv, q.x, q.y);
+                    sts_c2(&xx[row * TILE + k1B * ROWP + lo], zv);
+                }
+                tq[0] = tqn[0];
+                tq[1] = tqn[1];
+            }
+        };
+        // stages B, C and the X-engine of the frame held in exchange plane `buf`
+        auto fft_rest = [&](int buf) {
+            float4 *xx = sm.X[buf];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds_c2(&xx[k1B * TILE + n2 * ROWP + lo]);
+            dft16(v);
+            __syncwarp();
+            {
+                float4 tq[2], tqn[2];
+                tq[0] = sm.twB[0][lo];
+                tq[1] = sm.twB[1][lo];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < 3) {
+                        tqn[0] = sm.twB[2 * g + 2][lo];
+                        tqn[1] = sm.twB[2 * g + 3][lo];
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int k2 = g + 4 * b;
+                        C2 zv = v[4 * g + b];
+                        const float4 q = tq[b >> 1];
+                        if (k2 != 0) zv = (b & 1) ? cmuls(zv, q.z, q.w) : cmuls(zv, q.x, q.y);
+                        sts_c2(&xx[k1B * TILE + k2 * ROWP + lo], zv);
+                    }
+                    tq[0] = tqn[0];
+                    tq[1] = tqn[1];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = lds_c2(&xx[k1B * TILE + lo * ROWP + n3]);
+            dft16(v);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
+                accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
+                accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
+                acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+            }
+        };
+
+#pragma unroll 1
+        for (int s = 0; s <= sg.nf; ++s) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (half == grp) {
+                    if (s < sg.nf) stage_a(s, s & 1);
+                } else {
+                    if (s >= 1) fft_rest((s - 1) & 1);
+                }
+            }
+            __syncthreads();
+        }
+
+        // epilogue: bin k2 + 16*lo... in the fused kernel's order, k2 index = k1B + 16*lo + 256*perm16(jj)
+        {
+            float2 *xs = reinterpret_cast<float2 *>(&sm.X[0][0]);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const int idx = k1B + 16 * lo + 256 * perm16(jj);
+                const int sw = idx ^ ((idx >> 4) & 15);
+                sts_pair(&xs[sw], accx[jj]);
+                sts_pair(&xs[N + sw], acca[jj]);
+            }
+            __syncthreads();
+            float2 *px = prm.part_x + (long long)seg * N;
+            float2 *pa = prm.part_a + (long long)seg * N;
+#pragma unroll
+            for (int q = 0; q < N / NT; ++q) {
+                const int o = t + NT * q;
+                const int sw = o ^ ((o >> 4) & 15);
+                px[o] = xs[sw];
+                pa[o] = xs[N + sw];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- finalize ---------------------------------------------------------------------------------------
+// out[b][j] = conj(rot[c]) * (1/P) * sum over the segments of virtual block (b, k1) of part_x[s][k2],
+// c = (j + NB/2) mod NB = k1 + G*k2.   grid = (NB/256, n_blocks)
+__global__ void __launch_bounds__(256) finalize_kernel(const float2 *__restrict__ part_x,
+                                                       const float2 *__restrict__ part_a, int NB, int logG,
+                                                       const int *__restrict__ vblk_first, float inv_frames,
+                                                       const float2 *__restrict__ rot, float2 *__restrict__ xspec,
+                                                       float *__restrict__ auto0, float *__restrict__ auto1) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= NB) return;
+    const int c = (j + (NB >> 1)) & (NB - 1);
+    const int k1 = c & ((1 << logG) - 1), k2 = c >> logG;
+    const int vb = (b << logG) + k1;
+    float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int s = vblk_first[vb]; s < vblk_first[vb + 1]; ++s) {
+        const float2 x = part_x[(long long)s * N + k2];
+        const float2 a = part_a[(long long)s * N + k2];
+        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+    }
+    xr *= inv_frames; xi *= inv_frames;
+    const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);
+    xspec[(long long)b * NB + j] = make_float2(xr * r.x + xi * r.y, xi * r.x - xr * r.y);
+    if (auto0) auto0[(long long)b * NB + j] = a0 * inv_frames;
+    if (auto1) auto1[(long long)b * NB + j] = a1 * inv_frames;
+}
+
+}  // namespace bigfft
+}  // namespace fx
