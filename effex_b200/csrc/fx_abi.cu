@@ -324,12 +324,12 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         const long long nb = std::min(chunk, n_blocks - b0);
         const uint8_t *c0 = d_iq0 + 2 * S * b0, *c1 = d_iq1 + 2 * S * b0;
         const unsigned long long *su = h->d_sums + 4 * b0;
-        dim3 hg(fx::fused4096::N / 256, (unsigned)P, (unsigned)nb);
+        dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((P + kHeadFrames - 1) / kHeadFrames), (unsigned)nb);
         switch (h->logG) {
-            case 1: head_kernel<1><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            case 2: head_kernel<2><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            case 3: head_kernel<3><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            default: head_kernel<4><<<hg, 256, 0, h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
         }
         FX_LAUNCH_CHECK(h, "bigfft_head");
         h->planning_big = true;
@@ -779,6 +779,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                  (const void *)fused_kernel_stag<4>};
             CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         }
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::bigfft::SmemT)));
         // the lock-step cross-check kernel exists for 4096 bins only

@@ -5,9 +5,9 @@
 //
 //   X[k1 + G*k2] = sum_n2 W4096^(n2*k2) * [ W_N^(n2*k1) * sum_n1 w[n1*4096 + n2] * W_G^(n1*k1) ]
 //
-//   head_kernel   unpack + DC removal + 4-tap direct-form FIR for the G samples {n1*4096 + n2} of a thread,
-//                 G-point DFT in registers, twiddle W_N^(n2*k1)  ->  Z[block][frame][k1][n2]  (16 B: both
-//                 channels, re/im), written once, read once
+//   head_kernel   unpack + DC removal + 4-tap FIR (transposed form, state in registers) per polyphase position,
+//                 G-point DFT over n1 in registers, twiddle W_N^(n2*k1)  ->  Z[block][frame][k1][n2]  (16 B:
+//                 both channels, re/im), written once, read once
 //   tail_kernel   the fused kernel's stages A, B, C and X-engine (fx_fused4096s.cuh: staggered warp
 //                 groups, padded exchange tiles, packed FP32) with stage A fed from Z instead of the FIR;
 //                 a "virtual block" is (block, k1): its 4096 accumulated bins are k1 + G*k2
@@ -29,56 +29,99 @@ using fused4096::Segment;
 using fused4096::TILE;
 
 // ---- head ------------------------------------------------------------------------------------------
-// grid = (4096/256, P, n_blocks), 256 threads; thread = one n2, all G values of n1
+// A CTA owns 256 polyphase positions -- a tile of TN2 = 256/G consecutive n2 for all G values of n1 --
+// and walks kHeadFrames consecutive frames of one block (plus 3 frames of warm-up when it does not start
+// at the block's first frame).  Two phases per batch of G frames:
+//   1. thread = position: raw bytes of the batch are loaded up front (one uchar2 per channel per frame),
+//      unpacked ONCE (PRMT into the mantissa of 2^15, as in the fused kernel) and pushed through the
+//      transposed-form FIR whose state (z1..z3) stays in registers; FIR outputs go to shared memory;
+//   2. thread = (frame of the batch, n2): G-point DFT over n1 in registers, twiddle W_N^(n2*k1), and one
+//      16-byte store per k1 into Z (256-byte runs per warp half).
+// grid = (4096/TN2, ceil(P/kHeadFrames), n_blocks), 256 threads, dynamic smem G*4 KB
+constexpr int kHeadFrames = 32;
 template <int LOGG>
-__global__ void __launch_bounds__(256) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
+__global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
                                                    long long S, int P, const float *__restrict__ taps,
                                                    const unsigned long long *__restrict__ sums, int dc_remove,
                                                    float4 *__restrict__ z) {
+    using fused4096::byte_to_magic;
+    using fused4096::kMagic;
     constexpr int G = 1 << LOGG;
     constexpr int NB = N << LOGG;                  // nbins
-    const int n2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y, b = blockIdx.z;
-    __shared__ float s_mean[4];                    // byte means: ch0 I, ch0 Q, ch1 I, ch1 Q
-    if (threadIdx.x < 4) {
-        s_mean[threadIdx.x] = dc_remove ? (float)((double)sums[4ll * b + threadIdx.x] / (double)S) : 127.5f;
-    }
+    constexpr int TN2 = 256 >> LOGG;               // n2 values per CTA
+    extern __shared__ __align__(16) unsigned char head_smem[];
+    float4(*W)[256] = reinterpret_cast<float4(*)[256]>(head_smem);        // [G][256] FIR outputs of a batch
+    __shared__ float s_nm[4];                      // 128 - byte mean: ch0 I, ch0 Q, ch1 I, ch1 Q
+    const int t = threadIdx.x;
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * kHeadFrames;
+    const int i1 = min(i0 + kHeadFrames, P);
+    if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)S) : 0.5f;
     __syncthreads();
-    const float2 mI = f2(s_mean[0], s_mean[2]), mQ = f2(s_mean[1], s_mean[3]);
-    const uchar2 *x0 = reinterpret_cast<const uchar2 *>(iq0) + (long long)b * S;
-    const uchar2 *x1 = reinterpret_cast<const uchar2 *>(iq1) + (long long)b * S;
-    C2 v[G];
-    const int kmax = i < 3 ? i : 3;                // zero history before frame 0 of the block
+    const float2 nmI = f2(s_nm[0], s_nm[2]), nmQ = f2(s_nm[1], s_nm[3]);
+    const float2 mg = f2(-kMagic, -kMagic);
+    // phase-1 role: position (n1, n2)
+    const int n1 = t / TN2, n2 = blockIdx.x * TN2 + t % TN2;
+    const int n = n1 * N + n2;
+    const unsigned short *x0 = reinterpret_cast<const unsigned short *>(iq0) + (long long)b * S + n;
+    const unsigned short *x1 = reinterpret_cast<const unsigned short *>(iq1) + (long long)b * S + n;
+    const float t0 = taps[n], t1 = taps[(long long)NB + n], t2 = taps[2ll * NB + n], t3 = taps[3ll * NB + n];
+    float2 z1r = f2(0.f, 0.f), z1i = z1r, z2r = z1r, z2i = z1r, z3r = z1r, z3i = z1r;
+    // one sample through the FIR; returns the output of its frame
+    auto push = [&](uint32_t w) -> C2 {
+        const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
+        const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
+        const C2 out = {f2fmas(yr, t0, z1r), f2fmas(yi, t0, z1i)};
+        z1r = f2fmas(yr, t1, z2r); z1i = f2fmas(yi, t1, z2i);
+        z2r = f2fmas(yr, t2, z3r); z2i = f2fmas(yi, t2, z3i);
+        z3r = f2muls(yr, t3);      z3i = f2muls(yi, t3);
+        return out;
+    };
+    auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i at this position
+        const long long s = (long long)i * NB;
+        return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
+    };
+    for (int i = max(i0 - 3, 0); i < i0; ++i) push(raw(i));       // warm-up: history of the first frame
+    // phase-2 role: (frame slot, n2)
+    const int fs = t / TN2, j2 = t % TN2;
+    const int m2 = blockIdx.x * TN2 + j2;
+    for (int ib = i0; ib < i1; ib += G) {
+        uint32_t w[G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int n = g * N + n2;
-        float2 ar = f2(0.f, 0.f), ai = f2(0.f, 0.f);
-        for (int k = 0; k <= kmax; ++k) {
-            const long long s = (long long)(i - k) * NB + n;
-            const uchar2 a = x0[s], c = x1[s];
-            const float h = taps[(long long)k * NB + n];
-            ar = f2fmas(f2sub(f2((float)a.x, (float)c.x), mI), h, ar);
-            ai = f2fmas(f2sub(f2((float)a.y, (float)c.y), mQ), h, ai);
-        }
-        v[g] = {ar, ai};
-    }
-    if constexpr (G == 16) {
-        C2(&v16)[16] = reinterpret_cast<C2(&)[16]>(v);
-        dft16(v16);
-    } else {
-        fused4096::dft_small<G>(v);
-    }
-    float4 *zf = z + ((long long)b * P + i) * (long long)NB + n2;
+        for (int f = 0; f < G; ++f) w[f] = ib + f < i1 ? raw(ib + f) : 0u;
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-        const int k1 = fused4096::perm_rp(G, j);
-        C2 y = v[j];
-        if (k1 != 0) {
-            float sn, cs;
-            sincospif(-2.f * (float)((n2 * k1) & (NB - 1)) / (float)NB, &sn, &cs);     // exact argument
-            y = cmuls(y, cs, sn);
+        for (int f = 0; f < G; ++f) {
+            const C2 o = push(w[f]);
+            W[f][t] = make_float4(o.r.x, o.r.y, o.i.x, o.i.y);
         }
-        zf[(long long)k1 * N] = make_float4(y.r.x, y.r.y, y.i.x, y.i.y);
+        __syncthreads();
+        if (ib + fs < i1) {
+            C2 v[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 q = W[fs][g * TN2 + j2];
+                v[g] = {f2(q.x, q.y), f2(q.z, q.w)};
+            }
+            if constexpr (G == 16) {
+                C2(&v16)[16] = reinterpret_cast<C2(&)[16]>(v);
+                dft16(v16);
+            } else {
+                fused4096::dft_small<G>(v);
+            }
+            float4 *zf = z + ((long long)b * P + ib + fs) * (long long)NB + m2;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int k1 = fused4096::perm_rp(G, j);
+                C2 y = v[j];
+                if (k1 != 0) {
+                    float sn, cs;
+                    sincospif(-2.f * (float)((m2 * k1) & (NB - 1)) / (float)NB, &sn, &cs);     // exact argument
+                    y = cmuls(y, cs, sn);
+                }
+                __stcs(zf + (long long)k1 * N, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
+            }
+        }
+        __syncthreads();
     }
 }
 

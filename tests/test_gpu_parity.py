@@ -243,6 +243,54 @@ def test_fused_small_nbins_integrate_and_host_pipeline(S, N):
     eng.close()
 
 
+# --------------------------------------------------------------------------
+# nbins = G * 4096 (G = 2..16): head kernel -> Z -> tail kernel (fx_bigfft.cuh)
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("S,N,nb", [(3 * 8192, 8192, 3), (5 * 16384 + 24, 16384, 2), (2 * 32768, 32768, 2),
+                                    (4 * 65536, 65536, 2), (65536, 65536, 5), (2**18, 8192, 40)])
+def test_big_nbins_vs_oracle_and_generic(S, N, nb):
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=3, dc0=0.013 - 0.02j, dc1=-0.006 + 0.004j, seed=6)
+    bw, fc, tau = 2.4e6, 1.4204e9, 3 / 2.4e6
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    eng.set_delay(bw, fc, tau)
+    eng.reset_counters()
+    x, a0, a1 = eng.process(dev(raw0), dev(raw1), nb, autos=True)
+    assert eng.kernel_launches() <= 8, "expected the head/tail kernels, not one launch per FFT pass"
+    x, a0, a1 = x.cpu().numpy(), a0.cpu().numpy(), a1.cpu().numpy()
+    gen = FxEngine(S, N, 4, max_blocks=nb, force_generic=True)
+    gen.set_delay(bw, fc, tau)
+    xg, g0, g1 = gen.process(dev(raw0), dev(raw1), nb, autos=True)
+    xg, g0, g1 = xg.cpu().numpy(), g0.cpu().numpy(), g1.cpu().numpy()
+    check = range(nb) if nb <= 5 else [0, 1, nb // 2, nb - 1]
+    for b in check:
+        ref = orc.process_recording_u8(raw0, raw1, S, N, bw, fc, tau, 4, b, 1)[0]
+        assert_close(x[b], ref, what=f"S={S} N={N} block {b} vs oracle")
+        r0, r1 = oracle_autos(raw0, raw1, S, N, b)
+        assert np.abs(a0[b] - r0).max() <= TOL * r0.max() and np.abs(a1[b] - r1).max() <= TOL * r1.max()
+    # against the unfused kernels (independent code, same arithmetic type, different summation orders)
+    assert np.abs(x - xg).max() <= 1e-5 * np.abs(xg).max()
+    assert np.abs(a0 - g0).max() <= 1e-5 * g0.max() and np.abs(a1 - g1).max() <= 1e-5 * g1.max()
+    # with accumulators the same handle takes the unfused kernels: same rows
+    acc = eng.new_accumulators()
+    xa = eng.process(dev(raw0), dev(raw1), nb, acc=acc).cpu().numpy()
+    assert np.abs(xa - x).max() <= 1e-5 * np.abs(x).max()
+    eng.close(); gen.close()
+
+
+def test_big_nbins_several_chunks_of_Z():
+    """More blocks than one Z buffer (1 GiB) holds: 20 blocks of 2^22 samples at 65536 bins -> two chunks."""
+    S, N, nb = 2**22, 65536, 20
+    raw0, raw1 = synth.tiled_recording(nb, S, base_blocks=3)
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    x = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    for b in (0, 17):
+        ref = orc.process_recording_u8(raw0, raw1, S, N, 2.4e6, 1.4204e9, 0.0, 4, b, 1)[0]
+        assert_close(x[b], ref, what=f"block {b} vs oracle")
+    for b in range(3, nb):                       # tiled input: block b repeats block b mod 3
+        assert_close(x[b], x[b % 3], tol=2e-6, what=f"block {b} vs block {b % 3}")
+    eng.close()
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_golden_reference_fixture(golden_dir, tag):
     """Fixtures made by running the reference's own effex.py (tests/golden/make_golden.py)."""
