@@ -33,6 +33,7 @@ struct fx_handle {
     bool planning_big = false; // plan_segments is being called for virtual blocks of the big path
     bool big = false;          // nbins = 2^logG * 4096, ntaps = 4: head + tail kernels (fx_bigfft.cuh)
     int logG = 0;
+    float2 *d_twH = nullptr;   // big path: W_nbins^(n2*k1), [G][4096]
     float4 *d_z = nullptr;     // big path: Z[blocks of a chunk][P][G][4096]
     size_t z_cap = 0;          // in float4 elements
     int logF = 0;     // fused kernel: frames per 4096-sample super-frame = 2^logF (nbins = 4096 >> logF)
@@ -326,10 +327,10 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         const unsigned long long *su = h->d_sums + 4 * b0;
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((P + kHeadFrames - 1) / kHeadFrames), (unsigned)nb);
         switch (h->logG) {
-            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
-            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_z); break;
+            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
+            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
+            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
+            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
         }
         FX_LAUNCH_CHECK(h, "bigfft_head");
         h->planning_big = true;
@@ -779,6 +780,17 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                  (const void *)fused_kernel_stag<4>};
             CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         }
+        if (h->big) {
+            const int G = 1 << h->logG, NB = cfg->nbins;
+            std::vector<float2> twH((size_t)G * fx::fused4096::N);
+            for (int k1 = 0; k1 < G; ++k1)
+                for (int n2 = 0; n2 < fx::fused4096::N; ++n2) {
+                    const double a = -2.0 * M_PI * (double)(((long long)k1 * n2) % NB) / (double)NB;
+                    twH[(size_t)k1 * fx::fused4096::N + n2] = make_float2((float)cos(a), (float)sin(a));
+                }
+            CREATE_CUDA(cudaMalloc(&h->d_twH, twH.size() * sizeof(float2)));
+            CREATE_CUDA(cudaMemcpy(h->d_twH, twH.data(), twH.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::bigfft::SmemT)));
@@ -798,7 +810,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_twH, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

@@ -35,7 +35,7 @@ using fused4096::TILE;
 //   1. thread = position: raw bytes of the batch are loaded up front (one uchar2 per channel per frame),
 //      unpacked ONCE (PRMT into the mantissa of 2^15, as in the fused kernel) and pushed through the
 //      transposed-form FIR whose state (z1..z3) stays in registers; FIR outputs go to shared memory;
-//   2. thread = (frame of the batch, n2): G-point DFT over n1 in registers, twiddle W_N^(n2*k1), and one
+//   2. thread = (frame of the batch, n2): G-point DFT over n1 in registers, twiddle W_N^(n2*k1) (table), and one
 //      16-byte store per k1 into Z (256-byte runs per warp half).
 // grid = (4096/TN2, ceil(P/kHeadFrames), n_blocks), 256 threads, dynamic smem G*4 KB
 constexpr int kHeadFrames = 32;
@@ -43,7 +43,7 @@ template <int LOGG>
 __global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
                                                    long long S, int P, const float *__restrict__ taps,
                                                    const unsigned long long *__restrict__ sums, int dc_remove,
-                                                   float4 *__restrict__ z) {
+                                                   const float2 *__restrict__ twh, float4 *__restrict__ z) {
     using fused4096::byte_to_magic;
     using fused4096::kMagic;
     constexpr int G = 1 << LOGG;
@@ -114,9 +114,8 @@ __global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict_
                 const int k1 = fused4096::perm_rp(G, j);
                 C2 y = v[j];
                 if (k1 != 0) {
-                    float sn, cs;
-                    sincospif(-2.f * (float)((m2 * k1) & (NB - 1)) / (float)NB, &sn, &cs);     // exact argument
-                    y = cmuls(y, cs, sn);
+                    const float2 w = twh[k1 * N + m2];          // W_N^(n2*k1), host-built table (L2 resident)
+                    y = cmuls(y, w.x, w.y);
                 }
                 __stcs(zf + (long long)k1 * N, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
             }

@@ -71,8 +71,10 @@ int fx_destroy(fx_handle *h);
 const char *fx_last_error(const fx_handle *h);
 int fx_sync(fx_handle *h);
 /* 1 if fx_process on this handle runs the fused unpack->PFB->FFT->X kernel: ntaps == 4, nbins a power
- * of two in [256, 4096], num_samp a multiple of 8 and 16-byte aligned inputs.  Every other shape
- * (ntaps up to 32, nbins 8..65536, ragged num_samp, unaligned pointers) runs the unfused kernels. */
+ * of two in [256, 4096], num_samp a multiple of 8 and 16-byte aligned inputs.  ntaps == 4 with nbins in
+ * [8192, 65536] runs two kernels around one intermediate (fx_bigfft.cuh; returns 0 here).  Every other
+ * shape (ntaps up to 32, nbins 8..128, ragged num_samp, unaligned pointers, integrations above 4096
+ * bins) runs the unfused kernels. */
 int fx_uses_fused(const fx_handle *h);
 
 /* ---- parameters --------------------------------------------------------
