@@ -305,7 +305,7 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
 
 // nbins = G*4096: head kernel -> Z -> tail kernel -> rows, a chunk of blocks at a time (Z <= 1 GiB)
 int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
-            float *d_auto0, float *d_auto1) {
+            float *d_auto0, float *d_auto1, double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames) {
     using namespace fx::bigfft;
     const int NB = h->cfg.nbins, G = 1 << h->logG, P = h->P;
     const long long S = h->cfg.num_samp;
@@ -348,6 +348,17 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         FX_LAUNCH_CHECK(h, "bigfft_tail");
         rc = end_timed(h, ep);
         if (rc) return rc;
+        if (d_acc_x) {
+            if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)NB));
+            const int groups = (int)std::max<long long>(1, std::min<long long>(64, nb));
+            integrate_kernel<<<dim3((NB + 255) / 256, groups), 256, 0, h->stream>>>(
+                h->d_part_x, h->d_part_a, NB, h->logG, h->d_plan + h->off_blk, (int)nb, h->d_int_scratch);
+            FX_LAUNCH_CHECK(h, "bigfft_integrate");
+            fx::generic::integrate_stage2_kernel<<<(4 * NB + 255) / 256, 256, 0, h->stream>>>(
+                h->d_int_scratch, NB, groups, (double)nb * (double)P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+            FX_LAUNCH_CHECK(h, "integrate_stage2");
+        }
+        if (!d_xspec) continue;
         dim3 fg((NB + 255) / 256, (unsigned)nb);
         finalize_kernel<<<fg, 256, 0, h->stream>>>(h->d_part_x, h->d_part_a, NB, h->logG, h->d_plan + h->off_blk,
                                                    1.0f / (float)P, h->rot_set ? h->d_rot : nullptr,
@@ -529,8 +540,8 @@ PassOpts block_opts(const fx_handle *h, long long n_blocks) {
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
                    float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
                    double *d_acc_a1 = nullptr, double *d_frames = nullptr, const PassOpts *span = nullptr) {
-    if (h->big && !span && d_xspec && !d_acc_x && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
-        return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1);
+    if (h->big && !span && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
+        return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
     const PassOpts o = span ? *span : block_opts(h, n_blocks);
     int rc = run_parts(h, d_iq0, d_iq1, o);
     if (rc) return rc;

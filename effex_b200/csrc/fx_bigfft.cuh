@@ -312,5 +312,33 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float2 *__restrict_
     if (auto1) auto1[(long long)b * NB + j] = a1 * inv_frames;
 }
 
+// ---- integrate --------------------------------------------------------------------------------------
+// float64 partial sums of the un-normalised spectra over the blocks of group g, natural bin order, in the
+// layout integrate_stage2_kernel folds: scratch[g][ 2c, 2c+1 | 2NB + c | 3NB + c ].   grid = (NB/256, groups)
+__global__ void __launch_bounds__(256) integrate_kernel(const float2 *__restrict__ part_x,
+                                                        const float2 *__restrict__ part_a, int NB, int logG,
+                                                        const int *__restrict__ vblk_first, int n_blocks,
+                                                        double *__restrict__ scratch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= NB) return;
+    const int k1 = c & ((1 << logG) - 1), k2 = c >> logG;
+    const int groups = gridDim.y, g = blockIdx.y;
+    const int b0 = (int)((long long)n_blocks * g / groups), b1 = (int)((long long)n_blocks * (g + 1) / groups);
+    double xr = 0, xi = 0, a0 = 0, a1 = 0;
+    for (int b = b0; b < b1; ++b) {
+        const int vb = (b << logG) + k1;
+        for (int s = vblk_first[vb]; s < vblk_first[vb + 1]; ++s) {
+            const float2 x = part_x[(long long)s * N + k2];
+            const float2 a = part_a[(long long)s * N + k2];
+            xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+        }
+    }
+    double *o = scratch + (long long)g * 4 * NB;
+    o[2 * c] = xr;
+    o[2 * c + 1] = xi;
+    o[2 * NB + c] = a0;
+    o[3 * NB + c] = a1;
+}
+
 }  // namespace bigfft
 }  // namespace fx

@@ -73,8 +73,7 @@ int fx_sync(fx_handle *h);
 /* 1 if fx_process on this handle runs the fused unpack->PFB->FFT->X kernel: ntaps == 4, nbins a power
  * of two in [256, 4096], num_samp a multiple of 8 and 16-byte aligned inputs.  ntaps == 4 with nbins in
  * [8192, 65536] runs two kernels around one intermediate (fx_bigfft.cuh; returns 0 here).  Every other
- * shape (ntaps up to 32, nbins 8..128, ragged num_samp, unaligned pointers, integrations above 4096
- * bins) runs the unfused kernels. */
+ * shape (ntaps up to 32, nbins 8..128, ragged num_samp, unaligned pointers) runs the unfused kernels. */
 int fx_uses_fused(const fx_handle *h);
 
 /* ---- parameters --------------------------------------------------------

@@ -270,10 +270,18 @@ def test_big_nbins_vs_oracle_and_generic(S, N, nb):
     # against the unfused kernels (independent code, same arithmetic type, different summation orders)
     assert np.abs(x - xg).max() <= 1e-5 * np.abs(xg).max()
     assert np.abs(a0 - g0).max() <= 1e-5 * g0.max() and np.abs(a1 - g1).max() <= 1e-5 * g1.max()
-    # with accumulators the same handle takes the unfused kernels: same rows
+    # rows + float64 accumulators in one call, and accumulators alone (fx_integrate)
     acc = eng.new_accumulators()
     xa = eng.process(dev(raw0), dev(raw1), nb, acc=acc).cpu().numpy()
-    assert np.abs(xa - x).max() <= 1e-5 * np.abs(x).max()
+    np.testing.assert_array_equal(xa, x)
+    acc2 = eng.new_accumulators()
+    eng.integrate(dev(raw0), dev(raw1), acc2, nb)
+    eng.sync()
+    assert acc["frames"].item() == acc2["frames"].item() == nb * (S // N)
+    for a in (acc, acc2):
+        xi, i0, i1 = FxEngine.finish_integration(a, rot=rot_vector(N, bw, fc, tau))
+        assert_close(xi, x.astype(np.complex128).mean(axis=0), tol=2e-6, what="integrated cross-spectrum vs mean of rows")
+        assert_close(i0, a0.astype(np.float64).mean(axis=0), tol=2e-6, what="integrated auto0")
     eng.close(); gen.close()
 
 
