@@ -427,7 +427,7 @@ int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, i
     if (rc) return rc;
     if (N <= 4096) {
         const int threads = std::max(32, std::min(512, N / 2));
-        const size_t smem = 2 * (size_t)N * sizeof(float2);
+        const size_t smem = 3 * (size_t)N * sizeof(float2);
         for (long long r0 = 0; r0 < rows; r0 += (1ll << 30)) {
             const long long nr = std::min<long long>(1ll << 30, rows - r0);
             fx::generic::fft_rows_kernel<<<(unsigned)nr, threads, smem, h->stream>>>(buf + r0 * N, buf + r0 * N, N, logN,
@@ -734,7 +734,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     }
     h->d_sums = h->d_sums_set[0];
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     2 * 4096 * (int)sizeof(float2)));
+                                     3 * 4096 * (int)sizeof(float2)));
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::stockham_radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * 256 * (fx::generic::kPassJ + 1) + 256) * (int)sizeof(float2)));
     if (h->fused || h->big) {

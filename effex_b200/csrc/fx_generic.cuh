@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) pfb_fir4_kernel(const void *__restrict__ 
 
 // ---------------------------------------------------------------------------
 // Batched forward/inverse FFT of length N = 2^logN <= 4096, one row per CTA,
-// radix-2 Stockham autosort in shared memory.  phase_post: multiply bin c by
+// radix-4 Stockham autosort stages in shared memory (twiddle table built once per row).  phase_post: multiply bin c by
 // exp(-2*pi*i*c/N) (SURVEY App. A.4 factor, so rows equal channelize_poly's).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out,
@@ -203,35 +203,61 @@ __global__ void __launch_bounds__(512) fft_rows_kernel(const float2 *__restrict_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
     float2 *bufB = bufA + N;
+    float2 *tw = bufB + N;                       // W_N^i, i < N
     const long long row = blockIdx.x;
     const float2 *src = in + row * N;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) bufA[j] = src[j];
-    __syncthreads();
-    const int half = N >> 1;
     const float sgn = inverse ? 1.f : -1.f;
-    for (int s = 0; s < logN; ++s) {
-        const int Ns = 1 << s;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        bufA[j] = src[j];
+        float sn, cs;
+        sincospif(sgn * 2.f * (float)j / (float)N, &sn, &cs);
+        tw[j] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    int ns = 1;
+    if (logN & 1) {                              // one radix-2 stage (ns = 1: no twiddles)
+        const int half = N >> 1;
         for (int j = threadIdx.x; j < half; j += blockDim.x) {
-            const int k = j & (Ns - 1);
-            float sn, cs;
-            sincospif(sgn * (float)k / (float)Ns, &sn, &cs);
-            const float2 v0 = bufA[j];
-            const float2 a = bufA[j + half];
-            const float2 v1 = make_float2(a.x * cs - a.y * sn, a.x * sn + a.y * cs);
-            const int j0 = ((j - k) << 1) + k;
-            bufB[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-            bufB[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+            const float2 v0 = bufA[j], v1 = bufA[j + half];
+            bufB[2 * j] = make_float2(v0.x + v1.x, v0.y + v1.y);
+            bufB[2 * j + 1] = make_float2(v0.x - v1.x, v0.y - v1.y);
         }
         __syncthreads();
-        float2 *tmp = bufA; bufA = bufB; bufB = tmp;
+        float2 *t = bufA; bufA = bufB; bufB = t;
+        ns = 2;
+    }
+    const int quarter = N >> 2;
+    for (; ns < N; ns <<= 2) {                   // radix-4 autosort stages
+        const int step = N / (4 * ns);
+        for (int b = threadIdx.x; b < quarter; b += blockDim.x) {
+            const int k = b & (ns - 1);
+            const float2 a0 = bufA[b];
+            float2 a1 = bufA[b + quarter], a2 = bufA[b + 2 * quarter], a3 = bufA[b + 3 * quarter];
+            if (k) {
+                const float2 w1 = tw[k * step], w2 = tw[2 * k * step], w3 = tw[3 * k * step];
+                a1 = make_float2(a1.x * w1.x - a1.y * w1.y, a1.x * w1.y + a1.y * w1.x);
+                a2 = make_float2(a2.x * w2.x - a2.y * w2.y, a2.x * w2.y + a2.y * w2.x);
+                a3 = make_float2(a3.x * w3.x - a3.y * w3.y, a3.x * w3.y + a3.y * w3.x);
+            }
+            const float2 s02 = make_float2(a0.x + a2.x, a0.y + a2.y), d02 = make_float2(a0.x - a2.x, a0.y - a2.y);
+            const float2 s13 = make_float2(a1.x + a3.x, a1.y + a3.y), d13 = make_float2(a1.x - a3.x, a1.y - a3.y);
+            const float2 rot = make_float2(-sgn * d13.y, sgn * d13.x);      // sgn*i*d13  (forward: W4 = -i)
+            const int o = ((b - k) << 2) + k;
+            bufB[o] = make_float2(s02.x + s13.x, s02.y + s13.y);
+            bufB[o + ns] = make_float2(d02.x + rot.x, d02.y + rot.y);
+            bufB[o + 2 * ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+            bufB[o + 3 * ns] = make_float2(d02.x - rot.x, d02.y - rot.y);
+        }
+        __syncthreads();
+        float2 *t = bufA; bufA = bufB; bufB = t;
     }
     float2 *dst = out + row * N;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         float2 v = bufA[j];
-        if (phase_post) {
-            float sn, cs;
-            sincospif(-2.f * (float)j / (float)N, &sn, &cs);
-            v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+        if (phase_post) {                        // exp(-2*pi*i*j/N) = forward W_N^j
+            const float2 w = tw[j];
+            const float wy = inverse ? -w.y : w.y;
+            v = make_float2(v.x * w.x - v.y * wy, v.x * wy + v.y * w.x);
         }
         dst[j] = v;
     }
