@@ -35,12 +35,16 @@ using fused4096::TILE;
 //   1. thread = position: raw bytes of the batch are loaded up front (one uchar2 per channel per frame),
 //      unpacked ONCE (PRMT into the mantissa of 2^15, as in the fused kernel) and pushed through the
 //      transposed-form FIR whose state (z1..z3) stays in registers; FIR outputs go to shared memory;
-//   2. thread = (frame of the batch, n2): G-point DFT over n1 in registers, twiddle W_N^(n2*k1) (table), and one
+//   2. thread = (frame of the batch, n2): G-point DFT over n1 in registers, twiddle W_N^(n2*k1) (host table,
+//      the CTA's slice staged in shared memory), the next batch's raw loads already in flight, and one
 //      16-byte store per k1 into Z (256-byte runs per warp half).
 // grid = (4096/TN2, ceil(P/kHeadFrames), n_blocks), 256 threads, dynamic smem G*4 KB
-constexpr int kHeadFrames = 32;
+constexpr int kHeadFrames = 64;
+#ifndef FX_HEAD_CTAS
+#define FX_HEAD_CTAS 2
+#endif
 template <int LOGG>
-__global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
+__global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
                                                    long long S, int P, const float *__restrict__ taps,
                                                    const unsigned long long *__restrict__ sums, int dc_remove,
                                                    const float2 *__restrict__ twh, float4 *__restrict__ z) {
@@ -52,11 +56,13 @@ __global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict_
     extern __shared__ __align__(16) unsigned char head_smem[];
     float4(*W)[256] = reinterpret_cast<float4(*)[256]>(head_smem);        // [G][256] FIR outputs of a batch
     __shared__ float s_nm[4];                      // 128 - byte mean: ch0 I, ch0 Q, ch1 I, ch1 Q
+    __shared__ float2 s_tw[G][TN2];                // W_N^(n2*k1) of this CTA's n2 tile (fixed for all its frames)
     const int t = threadIdx.x;
     const int b = blockIdx.z;
     const int i0 = blockIdx.y * kHeadFrames;
     const int i1 = min(i0 + kHeadFrames, P);
     if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)S) : 0.5f;
+    s_tw[t / TN2][t % TN2] = twh[(t / TN2) * N + blockIdx.x * TN2 + t % TN2];
     __syncthreads();
     const float2 nmI = f2(s_nm[0], s_nm[2]), nmQ = f2(s_nm[1], s_nm[3]);
     const float2 mg = f2(-kMagic, -kMagic);
@@ -81,20 +87,34 @@ __global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict_
         const long long s = (long long)i * NB;
         return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
     };
-    for (int i = max(i0 - 3, 0); i < i0; ++i) push(raw(i));       // warm-up: history of the first frame
     // phase-2 role: (frame slot, n2)
     const int fs = t / TN2, j2 = t % TN2;
     const int m2 = blockIdx.x * TN2 + j2;
-    for (int ib = i0; ib < i1; ib += G) {
-        uint32_t w[G];
+    uint32_t w[G];                                 // raw words of the current batch, loaded one batch ahead
+    {
+        // warm-up (history of the first frame) and first batch: all loads issued before the first use
+        uint32_t wu[3];
 #pragma unroll
-        for (int f = 0; f < G; ++f) w[f] = ib + f < i1 ? raw(ib + f) : 0u;
+        for (int k = 0; k < 3; ++k) wu[k] = i0 - 3 + k >= 0 ? raw(i0 - 3 + k) : 0u;
+#pragma unroll
+        for (int f = 0; f < G; ++f) w[f] = i0 + f < i1 ? raw(i0 + f) : 0u;
+        if (i0 >= 3) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) push(wu[k]);
+        } else {
+            for (int k = 3 - i0; k < 3; ++k) push(wu[k]);          // i0 = 0: zero history, nothing to push
+        }
+    }
+    for (int ib = i0; ib < i1; ib += G) {
 #pragma unroll
         for (int f = 0; f < G; ++f) {
             const C2 o = push(w[f]);
             W[f][t] = make_float4(o.r.x, o.r.y, o.i.x, o.i.y);
         }
         __syncthreads();
+        // next batch's bytes: in flight during phase 2
+#pragma unroll
+        for (int f = 0; f < G; ++f) w[f] = ib + G + f < i1 ? raw(ib + G + f) : 0u;
         if (ib + fs < i1) {
             C2 v[G];
 #pragma unroll
@@ -114,8 +134,8 @@ __global__ void __launch_bounds__(256, 2) head_kernel(const uint8_t *__restrict_
                 const int k1 = fused4096::perm_rp(G, j);
                 C2 y = v[j];
                 if (k1 != 0) {
-                    const float2 w = twh[k1 * N + m2];          // W_N^(n2*k1), host-built table (L2 resident)
-                    y = cmuls(y, w.x, w.y);
+                    const float2 wk = s_tw[k1][j2];
+                    y = cmuls(y, wk.x, wk.y);
                 }
                 __stcs(zf + (long long)k1 * N, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
             }
