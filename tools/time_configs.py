@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Device-resident throughput of the non-headline BASELINE configs (generic kernels) -- informational."""
+"""Device-resident throughput of the BASELINE configs and of every kernel family (fused 256..4096 bins,
+head/tail 8192..65536 bins, lag search) -- informational."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,6 +27,8 @@ run("N=1024 S=2^18", 262144, 1024, 550)
 run("N=2048", 262144, 2048, 550)
 run("N=512", 262144, 512, 550)
 run("N=256", 262144, 256, 550)
+run("N=8192", 262144, 8192, 550)
+run("N=16384", 2**20, 16384, 140)
 run("C3 hi-res line", 2**24, 65536, 2)
 n = 262144
 eng = FxEngine(n, 4096, 4, max_blocks=92)
