@@ -33,6 +33,7 @@ struct fx_handle {
     bool planning_big = false; // plan_segments is being called for virtual blocks of the big path
     bool big = false;          // nbins = 2^logG * 4096, ntaps = 4: head + tail kernels (fx_bigfft.cuh)
     int logG = 0;
+    uint8_t *d_halo_pad[2] = {nullptr, nullptr};   // fused path: the caller's halo, right-aligned in whole super-frames
     float2 *d_twH = nullptr;   // big path: W_nbins^(n2*k1), [G][4096]
     float4 *d_z = nullptr;     // big path: Z[blocks of a chunk][P][G][4096]
     size_t z_cap = 0;          // in float4 elements
@@ -278,7 +279,22 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
     prm.S = o.S; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
     prm.mean_count = o.mean_count > 0 ? o.mean_count : o.S;
-    prm.halo0 = o.halo0; prm.halo1 = o.halo1;
+    prm.halo0 = prm.halo1 = nullptr;
+    if (o.halo0) {
+        // the T-1 halo frames become the tail of ceil((T-1)/F) super-frames (what precedes them never
+        // reaches the 4-tap FIR's output, so the padding bytes are arbitrary)
+        const int F = 1 << h->logF, hsf = (fx::fused4096::T - 1 + F - 1) / F;
+        const size_t pad_bytes = (size_t)hsf * fx::fused4096::FRAME_BYTES;
+        const size_t halo_bytes = (size_t)(fx::fused4096::T - 1) * h->cfg.nbins * 2;
+        const uint8_t *src[2] = {o.halo0, o.halo1};
+        for (int c = 0; c < 2; ++c) {
+            if (!h->d_halo_pad[c]) FX_CUDA(h, cudaMalloc(&h->d_halo_pad[c], 3 * (size_t)fx::fused4096::FRAME_BYTES));
+            FX_CUDA(h, cudaMemsetAsync(h->d_halo_pad[c], 128, pad_bytes, h->stream));
+            FX_CUDA(h, cudaMemcpyAsync(h->d_halo_pad[c] + pad_bytes - halo_bytes, src[c], halo_bytes,
+                                       cudaMemcpyDeviceToDevice, h->stream));
+        }
+        prm.halo0 = h->d_halo_pad[0]; prm.halo1 = h->d_halo_pad[1];
+    }
     prm.P = (int)o.P; prm.Psf = (int)((o.P + (1ll << h->logF) - 1) >> h->logF);
     const int grid = h->plan_grid;
     h->parts_per_block = false;
@@ -524,10 +540,8 @@ bool fused_ok_for(const fx_handle *h, const void *a, const void *b) {
 }
 
 int run_parts(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
-    const bool halo_ok = ((reinterpret_cast<uintptr_t>(o.halo0) | reinterpret_cast<uintptr_t>(o.halo1)) & 15) == 0;
-    // halos: staggered kernel at 4096 bins only (a halo is T-1 frames, not a whole super-frame)
-    const bool kernel_ok = !o.halo0 || (h->staggered && h->logF == 0);
-    if (fused_ok_for(h, d_iq0, d_iq1) && halo_ok && kernel_ok && (o.S % 8) == 0) return run_fused(h, d_iq0, d_iq1, o);
+    const bool kernel_ok = !o.halo0 || h->staggered;      // the lock-step kernel has no halo path
+    if (fused_ok_for(h, d_iq0, d_iq1) && kernel_ok && (o.S % 8) == 0) return run_fused(h, d_iq0, d_iq1, o);
     return run_generic(h, d_iq0, d_iq1, o);
 }
 
@@ -821,7 +835,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_twH, h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

@@ -65,7 +65,8 @@ struct Params {
     float2 *part_a;                     // [n_segs][N] (sum|F0|^2, sum|F1|^2)
     long long S;                        // samples per block
     long long mean_count;               // samples the byte sums were taken over (= S unless recording-wide sums are supplied)
-    const uint8_t *halo0, *halo1;       // streaming mode: the (T-1) frames that precede frame 0 of block 0, or NULL
+    const uint8_t *halo0, *halo1;       // streaming mode: the (T-1) frames that precede frame 0 of block 0, right-aligned in
+                                        // ceil((T-1)/F) super-frames of 4096 samples (16-byte aligned), or NULL
     int n_segs;
     int dc_remove;
     int P;                              // frames per block

@@ -204,7 +204,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
         }
         // first ingested frame: T-1 frames before the first output frame; before frame 0 of block 0 only
         // when the caller supplied the preceding samples (streaming mode), otherwise zero history
-        // (segments count super-frames; the host passes halos only when F == 1)
+        // (segments count super-frames; the host hands over the T-1 halo frames right-aligned in HSF super-frames)
         const bool use_halo = prm.halo0 != nullptr && sg.block == 0 && sg.f0 < HSF;
         const int g0 = (use_halo || sg.f0 - HSF > 0) ? sg.f0 - HSF : 0;
         const int n_ing = sg.f0 + sg.nf - g0;
@@ -218,8 +218,8 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
             sm.src0 = b0 + (long long)g0 * FRAME_BYTES;        // ingest item j reads src + j*FRAME_BYTES ...
             sm.src1 = b1 + (long long)g0 * FRAME_BYTES;
             sm.n_halo = g0 < 0 ? -g0 : 0;                      // ... except the first n_halo items: halo frames
-            sm.hsrc0 = prm.halo0 + (long long)(T - 1 + g0) * FRAME_BYTES;
-            sm.hsrc1 = prm.halo1 + (long long)(T - 1 + g0) * FRAME_BYTES;
+            sm.hsrc0 = prm.halo0 + (long long)(HSF + g0) * FRAME_BYTES;      // halo buffer: HSF super-frames
+            sm.hsrc1 = prm.halo1 + (long long)(HSF + g0) * FRAME_BYTES;
             sm.nsrc0 = prm.iq0 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
             sm.nsrc1 = prm.iq1 + 2ll * prm.S * ng.block + (long long)ng0 * FRAME_BYTES;
             sm.g0 = g0;

@@ -118,7 +118,7 @@ def test_c5_short_integrations():
     eng.close()
 
 
-@pytest.mark.parametrize("S,N", [(2**16, 4096), (2**13, 1024)])
+@pytest.mark.parametrize("S,N", [(2**16, 4096), (2**13, 1024), (2**14, 2048), (2**12, 256), (2**15, 8192)])
 def test_streaming_history_equals_one_giant_block(S, N):
     """Streaming mode (PFB history carried across blocks, recording-wide mean) = the reference's
     arithmetic applied to the whole recording as ONE block; and cutting the recording into time shards
