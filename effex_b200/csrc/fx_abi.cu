@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -319,6 +320,16 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     return end_timed(h, ep);
 }
 
+// capacity of the Z buffer in float4 elements (1 GiB); EFFEX_FX_Z_ELEMS shrinks it so that tests can walk
+// several chunks with small inputs
+size_t z_budget() {
+    if (const char *e = getenv("EFFEX_FX_Z_ELEMS")) {
+        const long long v = atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return size_t(1) << 26;
+}
+
 // nbins = G*4096: head kernel -> Z -> tail kernel -> rows, a chunk of blocks at a time (Z <= 1 GiB)
 int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
             float *d_auto0, float *d_auto1, double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames) {
@@ -328,7 +339,7 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
     int rc = launch_sums(h, d_iq0, d_iq1, n_blocks, S);
     if (rc) return rc;
     const size_t per_block = (size_t)P * NB;                              // float4 elements of Z
-    long long chunk = (long long)std::max<size_t>(1, (size_t(1) << 26) / per_block);
+    long long chunk = (long long)std::max<size_t>(1, z_budget() / per_block);
     chunk = std::min<long long>(std::min<long long>(chunk, n_blocks), 65535 / G);
     if (chunk * per_block > h->z_cap) {
         if (h->d_z) cudaFree(h->d_z);
@@ -343,10 +354,10 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         const unsigned long long *su = h->d_sums + 4 * b0;
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((P + kHeadFrames - 1) / kHeadFrames), (unsigned)nb);
         switch (h->logG) {
-            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
-            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
-            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
-            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, P, h->d_taps_u8, su, h->cfg.dc_remove, h->d_twH, h->d_z); break;
+            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
         }
         FX_LAUNCH_CHECK(h, "bigfft_head");
         h->planning_big = true;
@@ -381,6 +392,64 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
                                                    reinterpret_cast<float2 *>(d_xspec) + b0 * NB,
                                                    d_auto0 ? d_auto0 + b0 * NB : nullptr, d_auto1 ? d_auto1 + b0 * NB : nullptr);
         FX_LAUNCH_CHECK(h, "bigfft_finalize");
+    }
+    return release_sums(h);
+}
+
+// streaming-history span at nbins = G*4096: ONE unit of o.P frames (recording-wide mean, halo frames),
+// walked in chunks of frames so that Z stays under 1 GiB; only the float64 accumulators are produced
+int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o, double *d_acc_x,
+                 double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+    using namespace fx::bigfft;
+    const int NB = h->cfg.nbins, G = 1 << h->logG;
+    const long long P = o.P;
+    int rc = prepare_sums(h, d_iq0, d_iq1, o);
+    if (rc) return rc;
+    const long long mean_count = o.mean_count > 0 ? o.mean_count : o.S;
+    long long fc = ((long long)z_budget() / NB / kHeadFrames) * kHeadFrames;             // frames per chunk
+    fc = std::max<long long>(kHeadFrames, std::min<long long>(fc, 65535ll * kHeadFrames));
+    const size_t need = (size_t)std::min<long long>(fc, P) * NB;
+    if (need > h->z_cap) {
+        if (h->d_z) cudaFree(h->d_z);
+        h->d_z = nullptr;
+        h->z_cap = 0;
+        FX_CUDA(h, cudaMalloc(&h->d_z, need * sizeof(float4)));
+        h->z_cap = need;
+    }
+    if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)NB));
+    for (long long ib = 0; ib < P; ib += fc) {
+        const int n = (int)std::min<long long>(fc, P - ib);
+        dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((n + kHeadFrames - 1) / kHeadFrames), 1);
+#define FX_HEAD_ARGS d_iq0, d_iq1, o.S, (int)ib, (int)ib + n, h->d_taps_u8, h->d_sums, h->cfg.dc_remove, mean_count, o.halo0, o.halo1, h->d_twH, h->d_z
+        switch (h->logG) {
+            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(FX_HEAD_ARGS); break;
+            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(FX_HEAD_ARGS); break;
+            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(FX_HEAD_ARGS); break;
+            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(FX_HEAD_ARGS); break;
+        }
+#undef FX_HEAD_ARGS
+        FX_LAUNCH_CHECK(h, "bigfft_head");
+        h->planning_big = true;
+        rc = plan_segments(h, G, n);                                      // virtual blocks (0, k1), n frames each
+        h->planning_big = false;
+        if (rc) return rc;
+        TailParams prm;
+        prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
+        prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
+        prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = n;
+        EventPair ep{};
+        rc = begin_timed(h, ep);
+        if (rc) return rc;
+        tail_kernel<<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
+        FX_LAUNCH_CHECK(h, "bigfft_tail");
+        rc = end_timed(h, ep);
+        if (rc) return rc;
+        integrate_kernel<<<dim3((NB + 255) / 256, 1), 256, 0, h->stream>>>(h->d_part_x, h->d_part_a, NB, h->logG,
+                                                                           h->d_plan + h->off_blk, 1, h->d_int_scratch);
+        FX_LAUNCH_CHECK(h, "bigfft_integrate");
+        fx::generic::integrate_stage2_kernel<<<(4 * NB + 255) / 256, 256, 0, h->stream>>>(
+            h->d_int_scratch, NB, 1, (double)n, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+        FX_LAUNCH_CHECK(h, "integrate_stage2");
     }
     return release_sums(h);
 }
@@ -554,6 +623,8 @@ PassOpts block_opts(const fx_handle *h, long long n_blocks) {
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
                    float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
                    double *d_acc_a1 = nullptr, double *d_frames = nullptr, const PassOpts *span = nullptr) {
+    if (h->big && span && d_acc_x && !d_xspec && span->P <= 0x7fffffffll && (span->S & 1) == 0)
+        return run_big_span(h, d_iq0, d_iq1, *span, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
     if (h->big && !span && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
         return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
     const PassOpts o = span ? *span : block_opts(h, n_blocks);

@@ -45,9 +45,11 @@ constexpr int kHeadFrames = 64;
 #endif
 template <int LOGG>
 __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
-                                                   long long S, int P, const float *__restrict__ taps,
+                                                   long long S, int i_begin, int i_end, const float *__restrict__ taps,
                                                    const unsigned long long *__restrict__ sums, int dc_remove,
-                                                   const float2 *__restrict__ twh, float4 *__restrict__ z) {
+                                                   long long mean_count, const uint8_t *__restrict__ halo0,
+                                                   const uint8_t *__restrict__ halo1, const float2 *__restrict__ twh,
+                                                   float4 *__restrict__ z) {
     using fused4096::byte_to_magic;
     using fused4096::kMagic;
     constexpr int G = 1 << LOGG;
@@ -59,9 +61,11 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
     __shared__ float2 s_tw[G][TN2];                // W_N^(n2*k1) of this CTA's n2 tile (fixed for all its frames)
     const int t = threadIdx.x;
     const int b = blockIdx.z;
-    const int i0 = blockIdx.y * kHeadFrames;
-    const int i1 = min(i0 + kHeadFrames, P);
-    if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)S) : 0.5f;
+    // frames [i_begin, i_end) of the block go to Z rows 0 .. i_end - i_begin (reference mode: the whole block;
+    // streaming mode: one chunk of the span, mean over mean_count samples, halo = the 3 frames before frame 0)
+    const int i0 = i_begin + blockIdx.y * kHeadFrames;
+    const int i1 = min(i0 + kHeadFrames, i_end);
+    if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)mean_count) : 0.5f;
     s_tw[t / TN2][t % TN2] = twh[(t / TN2) * N + blockIdx.x * TN2 + t % TN2];
     __syncthreads();
     const float2 nmI = f2(s_nm[0], s_nm[2]), nmQ = f2(s_nm[1], s_nm[3]);
@@ -84,9 +88,15 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         return out;
     };
     auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i at this position
+        if (i < 0) {                               // streaming mode: frames -3..-1 come from the halo
+            const long long s = (long long)(i + 3) * NB + n;
+            return (uint32_t)reinterpret_cast<const unsigned short *>(halo0)[s] |
+                   ((uint32_t)reinterpret_cast<const unsigned short *>(halo1)[s] << 16);
+        }
         const long long s = (long long)i * NB;
         return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
     };
+    const int first_hist = halo0 ? -3 : 0;         // earliest frame that exists
     // phase-2 role: (frame slot, n2)
     const int fs = t / TN2, j2 = t % TN2;
     const int m2 = blockIdx.x * TN2 + j2;
@@ -95,14 +105,14 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         // warm-up (history of the first frame) and first batch: all loads issued before the first use
         uint32_t wu[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wu[k] = i0 - 3 + k >= 0 ? raw(i0 - 3 + k) : 0u;
+        for (int k = 0; k < 3; ++k) wu[k] = i0 - 3 + k >= first_hist ? raw(i0 - 3 + k) : 0u;
 #pragma unroll
         for (int f = 0; f < G; ++f) w[f] = i0 + f < i1 ? raw(i0 + f) : 0u;
-        if (i0 >= 3) {
+        if (i0 - 3 >= first_hist) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) push(wu[k]);
         } else {
-            for (int k = 3 - i0; k < 3; ++k) push(wu[k]);          // i0 = 0: zero history, nothing to push
+            for (int k = 3 - (i0 - first_hist); k < 3; ++k) push(wu[k]);   // zero history before the first frame
         }
     }
     for (int ib = i0; ib < i1; ib += G) {
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
             } else {
                 fused4096::dft_small<G>(v);
             }
-            float4 *zf = z + ((long long)b * P + ib + fs) * (long long)NB + m2;
+            float4 *zf = z + ((long long)b * (i_end - i_begin) + (ib + fs - i_begin)) * (long long)NB + m2;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 const int k1 = fused4096::perm_rp(G, j);

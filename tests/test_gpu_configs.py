@@ -160,3 +160,39 @@ def test_streaming_history_equals_one_giant_block(S, N):
         xs, a0s, _ = FxEngine.finish_integration(tot)
         assert close(xs, ref) and close(xs, x, 2e-6) and close(a0s, a0, 2e-6), world
     eng.close()
+
+
+def test_big_nbins_streaming_and_rows_walk_several_chunks_of_Z(monkeypatch):
+    """8192 bins with the Z buffer limited to 64 frames: the streaming span (200 frames, halo, recording-wide
+    mean) is walked in four frame chunks and the block mode in block chunks; both equal the oracle."""
+    monkeypatch.setenv("EFFEX_FX_Z_ELEMS", str(64 * 8192))
+    S, N, nb = 25 * 8192, 8192, 8
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=7, dc0=0.02 + 0.01j, dc1=-0.015j, seed=23)
+    d0, d1 = dev(raw0), dev(raw1)
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    w = orc.pfb_window(4, N)
+    x0, x1 = orc.block_from_u8(raw0), orc.block_from_u8(raw1)          # ONE block: global mean
+    f0, f1 = orc.spectrometer_poly(x0, 4, N, w), orc.spectrometer_poly(x1, 4, N, w)
+    ref = np.fft.fftshift((f0 * np.conj(f1)).mean(axis=0))
+    acc = eng.new_accumulators()
+    eng.integrate_stream(d0, d1, acc, nb)
+    x, _, _ = FxEngine.finish_integration(acc)
+    assert acc["frames"].item() == nb * S // N == 200
+    assert close(x, ref)
+    # second half alone, with its halo and the recording-wide sums: adds up with the first half
+    sums = eng.span_sums(d0, d1, nb)
+    tot = eng.new_accumulators()
+    half = nb // 2
+    eng.integrate_stream(d0[:2 * S * half], d1[:2 * S * half], tot, half, sums=sums, total_samp=nb * S)
+    hb = 2 * 3 * N
+    lo = 2 * S * half
+    eng.integrate_stream(d0[lo:], d1[lo:], tot, nb - half, halo0=d0[lo - hb:lo], halo1=d1[lo - hb:lo], sums=sums,
+                         total_samp=nb * S)
+    xt, _, _ = FxEngine.finish_integration(tot)
+    assert close(xt, ref)
+    # block mode: 25 frames per block -> two blocks per chunk of Z
+    rows = eng.process(d0, d1, nb).cpu().numpy()
+    refr = orc.process_recording_u8(raw0, raw1, S, N, 2.4e6, 1.4204e9, 0.0, 4, 0, nb)
+    for b in range(nb):
+        assert close(rows[b], refr[b])
+    eng.close()
