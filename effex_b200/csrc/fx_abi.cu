@@ -354,10 +354,10 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         const unsigned long long *su = h->d_sums + 4 * b0;
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((P + kHeadFrames - 1) / kHeadFrames), (unsigned)nb);
         switch (h->logG) {
-            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
-            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
-            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
-            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            case 1: head_kernel<1, false><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            case 2: head_kernel<2, false><<<hg, 256, (4096u << 2), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            case 3: head_kernel<3, false><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
+            default: head_kernel<4, false><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
         }
         FX_LAUNCH_CHECK(h, "bigfft_head");
         h->planning_big = true;
@@ -422,10 +422,10 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((n + kHeadFrames - 1) / kHeadFrames), 1);
 #define FX_HEAD_ARGS d_iq0, d_iq1, o.S, (int)ib, (int)ib + n, h->d_taps_u8, h->d_sums, h->cfg.dc_remove, mean_count, o.halo0, o.halo1, h->d_twH, h->d_z
         switch (h->logG) {
-            case 1: head_kernel<1><<<hg, 256, (4096u << 1), h->stream>>>(FX_HEAD_ARGS); break;
-            case 2: head_kernel<2><<<hg, 256, (4096u << 2), h->stream>>>(FX_HEAD_ARGS); break;
-            case 3: head_kernel<3><<<hg, 256, (4096u << 3), h->stream>>>(FX_HEAD_ARGS); break;
-            default: head_kernel<4><<<hg, 256, (4096u << 4), h->stream>>>(FX_HEAD_ARGS); break;
+            case 1: head_kernel<1, true><<<hg, 256, (4096u << 1), h->stream>>>(FX_HEAD_ARGS); break;
+            case 2: head_kernel<2, true><<<hg, 256, (4096u << 2), h->stream>>>(FX_HEAD_ARGS); break;
+            case 3: head_kernel<3, true><<<hg, 256, (4096u << 3), h->stream>>>(FX_HEAD_ARGS); break;
+            default: head_kernel<4, true><<<hg, 256, (4096u << 4), h->stream>>>(FX_HEAD_ARGS); break;
         }
 #undef FX_HEAD_ARGS
         FX_LAUNCH_CHECK(h, "bigfft_head");
@@ -887,7 +887,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
             CREATE_CUDA(cudaMalloc(&h->d_twH, twH.size() * sizeof(float2)));
             CREATE_CUDA(cudaMemcpy(h->d_twH, twH.data(), twH.size() * sizeof(float2), cudaMemcpyHostToDevice));
         }
-        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::bigfft::SmemT)));
         // the lock-step cross-check kernel exists for 4096 bins only

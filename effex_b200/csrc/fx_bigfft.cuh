@@ -43,7 +43,9 @@ constexpr int kHeadFrames = 64;
 #ifndef FX_HEAD_CTAS
 #define FX_HEAD_CTAS 2
 #endif
-template <int LOGG>
+// SPAN = false: reference mode (whole blocks, i_begin = 0, per-block mean over S samples, zero history);
+// SPAN = true: a chunk of frames of one streaming span (mean over mean_count samples, optional halo)
+template <int LOGG, bool SPAN>
 __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *__restrict__ iq0, const uint8_t *__restrict__ iq1,
                                                    long long S, int i_begin, int i_end, const float *__restrict__ taps,
                                                    const unsigned long long *__restrict__ sums, int dc_remove,
@@ -63,9 +65,10 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
     const int b = blockIdx.z;
     // frames [i_begin, i_end) of the block go to Z rows 0 .. i_end - i_begin (reference mode: the whole block;
     // streaming mode: one chunk of the span, mean over mean_count samples, halo = the 3 frames before frame 0)
+    if (!SPAN) i_begin = 0;
     const int i0 = i_begin + blockIdx.y * kHeadFrames;
     const int i1 = min(i0 + kHeadFrames, i_end);
-    if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)mean_count) : 0.5f;
+    if (t < 4) s_nm[t] = dc_remove ? (float)(128.0 - (double)sums[4ll * b + t] / (double)(SPAN ? mean_count : S)) : 0.5f;
     s_tw[t / TN2][t % TN2] = twh[(t / TN2) * N + blockIdx.x * TN2 + t % TN2];
     __syncthreads();
     const float2 nmI = f2(s_nm[0], s_nm[2]), nmQ = f2(s_nm[1], s_nm[3]);
@@ -87,16 +90,17 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         z3r = f2muls(yr, t3);      z3i = f2muls(yi, t3);
         return out;
     };
-    auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i at this position
-        if (i < 0) {                               // streaming mode: frames -3..-1 come from the halo
-            const long long s = (long long)(i + 3) * NB + n;
-            return (uint32_t)reinterpret_cast<const unsigned short *>(halo0)[s] |
-                   ((uint32_t)reinterpret_cast<const unsigned short *>(halo1)[s] << 16);
-        }
+    auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i >= 0 at this position
         const long long s = (long long)i * NB;
         return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
     };
-    const int first_hist = halo0 ? -3 : 0;         // earliest frame that exists
+    auto raw_hist = [&](int i) -> uint32_t {       // warm-up only: frames -3..-1 come from the halo (streaming mode)
+        if (!SPAN || i >= 0) return raw(i);
+        const long long s = (long long)(i + 3) * NB + n;
+        return (uint32_t)reinterpret_cast<const unsigned short *>(halo0)[s] |
+               ((uint32_t)reinterpret_cast<const unsigned short *>(halo1)[s] << 16);
+    };
+    const int first_hist = (SPAN && halo0) ? -3 : 0;         // earliest frame that exists
     // phase-2 role: (frame slot, n2)
     const int fs = t / TN2, j2 = t % TN2;
     const int m2 = blockIdx.x * TN2 + j2;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         // warm-up (history of the first frame) and first batch: all loads issued before the first use
         uint32_t wu[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wu[k] = i0 - 3 + k >= first_hist ? raw(i0 - 3 + k) : 0u;
+        for (int k = 0; k < 3; ++k) wu[k] = i0 - 3 + k >= first_hist ? raw_hist(i0 - 3 + k) : 0u;
 #pragma unroll
         for (int f = 0; f < G; ++f) w[f] = i0 + f < i1 ? raw(i0 + f) : 0u;
         if (i0 - 3 >= first_hist) {
