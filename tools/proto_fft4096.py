@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """numpy emulation of the fused kernel's 16x16x16 FFT dataflow (thread = axis 0).
 
-Mirrors effex_b200/csrc/fx_fused4096.cu stage by stage: same register
-positions (digit-reversed radix-16 outputs), same twiddle tables, same
-exchange addresses including the XOR swizzle.  Run: python tools/proto_fft4096.py
+Mirrors effex_b200/csrc/fx_fused4096s.cuh stage by stage: same register positions (digit-reversed
+radix-16 outputs), same twiddle tables, same thread -> (tile, row, column) roles in the two exchanges.
+The exchange ADDRESSES here are those of the first version of the kernel (flat 256-element tiles with an
+XOR swizzle); the kernel now pads tile rows to 17 elements instead -- a different bijection onto shared
+memory, the same dataflow.  tools/proto_superframe.py covers nbins below and above 4096.
+Run: python tools/proto_fft4096.py
 """
 import numpy as np
 
