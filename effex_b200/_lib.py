@@ -16,6 +16,9 @@ FX_ERR_INVALID = -1
 FX_ERR_CUDA = -2
 FX_ERR_UNSUPPORTED = -3
 FX_ERR_STATE = -4
+FX_ERR_COMM = -5
+FX_ABI_VERSION = 2            # must equal FX_ABI_VERSION of include/effex_fx.h (checked in load())
+FX_COMM_TOKEN_BYTES = 128
 FX_FLAG_FORCE_GENERIC = 1
 FX_FLAG_LOCKSTEP_KERNEL = 2
 
@@ -43,6 +46,13 @@ SIGNATURES = {
     "fx_process_acc": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "fx_span_sums": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_uint64)]),
     "fx_integrate_stream": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, C.POINTER(C.c_uint64), C.c_int64, _VP, _VP, _VP, _VP]),
+    "fx_comm_export": (C.c_int, [_VP, C.c_int, C.c_size_t, _VP]),
+    "fx_comm_attach": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "fx_comm_fence": (C.c_int, [_VP]),
+    "fx_process_reduce": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, C.c_int, _VP]),
+    "fx_integrate_stream_reduce": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, C.POINTER(C.c_uint64), C.c_int64, C.c_int, _VP]),
+    "fx_reduce_f64": (C.c_int, [_VP, _VP, C.c_size_t, C.c_int]),
+    "fx_reduce_f32": (C.c_int, [_VP, _VP, C.c_size_t, C.c_int]),
     "fx_process_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "fx_pfb_c64": (C.c_int, [_VP, _VP, _VP]),
     "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),
@@ -73,9 +83,19 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    default_lib = "EFFEX_FX_LIB" not in os.environ
     if not os.path.exists(LIB_PATH):
         from . import build as _build          # raises if nvcc is missing
         _build.build()
+    elif default_lib:
+        # a stale binary would be called through mismatched argtypes: rebuild when the sources are newer
+        # and a compiler is here (a GPU box gets the prebuilt .so and usually the sources with it)
+        from . import build as _build
+        try:
+            if _build._stale():
+                _build.build()
+        except RuntimeError:
+            pass                               # no nvcc: the ABI version check below is the guard
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:                       # pragma: no cover - environment specific
@@ -85,5 +105,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)                # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
+    got = lib.fx_abi_version()
+    if got != FX_ABI_VERSION:
+        raise RuntimeError(f"libeffex_fx.so has ABI version {got}, this package binds version {FX_ABI_VERSION}: "
+                           "rebuild with `python -m effex_b200.build --force`")
     _lib = lib
     return lib

@@ -14,6 +14,8 @@
 #include "fx_fused4096s.cuh"
 #include "fx_generic.cuh"
 #include "fx_bigfft.cuh"
+#include "fx_comm.cuh"
+#include <unistd.h>
 
 namespace {
 
@@ -61,11 +63,23 @@ struct fx_handle {
     int sums_idx = 0;
     float2 *d_part_x = nullptr, *d_part_a = nullptr;
     size_t part_cap = 0;                      // in float2 elements per buffer
-    int *d_plan = nullptr;                     // [segments x4 | cta_first | blk_first]
-    size_t segs_cap = 0, off_cta = 0, off_blk = 0;
-    std::vector<fx::fused4096::Segment> h_segs;
-    std::vector<int> h_cta_first, h_blk_first;
-    long long planned_blocks = -1, planned_P = -1;
+    // segment plans: a small LRU of device-resident plans keyed by (units, P), each with its own pinned
+    // staging buffer, all sized in fx_create -- the hot calls never allocate, synchronise or copy blockingly
+    struct PlanSlot {
+        long long units = -1, P = -1;
+        int *d_plan = nullptr, *h_pin = nullptr;   // [segments x4 | cta_first | blk_first]
+        size_t n_segs = 0, off_cta = 0, off_blk = 0;
+        int grid = 0;
+        cudaEvent_t uploaded = nullptr;
+        bool upload_recorded = false;
+        unsigned long long last_use = 0;
+    };
+    static constexpr int kPlanSlots = 4;
+    PlanSlot plans[kPlanSlots];
+    size_t plan_cap = 0;                       // ints per slot
+    unsigned long long plan_clock = 0;
+    int *d_plan = nullptr;                     // the current plan (one of the slots)
+    size_t off_cta = 0, off_blk = 0, n_segs = 0;
     int plan_grid = 0;
     bool parts_per_block = false;              // generic path: one partial per block
 
@@ -85,6 +99,22 @@ struct fx_handle {
     float *d_out_x[2] = {nullptr, nullptr}, *d_out_a0[2] = {nullptr, nullptr}, *d_out_a1[2] = {nullptr, nullptr};
     int stage_blocks = 0;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    // cross-GPU reduce over peer memory (fx_comm.cuh)
+    struct Comm {
+        bool exported = false, attached = false;
+        int rank = 0, world = 1, ctas = 0;
+        size_t slot_bytes = 0, local_bytes = 0, off_done = 0, off_flags = 0, off_slots = 0;
+        char *local = nullptr;
+        char *peer[fx::comm::kMaxWorld] = {};
+        bool peer_ipc[fx::comm::kMaxWorld] = {};
+        unsigned int epoch = 0;
+        cudaStream_t stream_fold = nullptr;
+        cudaEvent_t ev_push = nullptr, ev_fold = nullptr;
+        bool fold_pending = false;
+        long long timeout_cycles = 20000000000ll;    // ~10 s at 1.965 GHz
+        double *d_acc_local = nullptr;               // [4N+1] staging for paths that run several stage-2 passes per call
+    } comm;
 
     std::string err;
     long long launches = 0;
@@ -194,56 +224,68 @@ int ensure_parts(fx_handle *h, size_t n_segs, size_t bins_per_seg = 0) {
 // Balanced contiguous partition: the n_blocks*P frames of the call are cut into `grid` equal
 // contiguous runs, one per persistent CTA; a run is a list of segments (pieces of blocks).  Only
 // the first segment of a run starts inside a block (and has to re-ingest T-1 frames of history).
+// Plans are cached per (n_blocks, P): a repeated shape costs a table lookup; a new shape is built into the
+// least recently used slot's pinned buffer and uploaded with an asynchronous copy on the handle's stream.
 int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
     if (P <= 0) P = h->P;
-    if (h->planned_blocks == n_blocks && h->planned_P == P) return FX_OK;
-    const long long planned_P = P;
-    P = (P + (1ll << h->logF) - 1) >> h->logF;       // the kernel walks super-frames of 2^logF frames
-    const long long F = n_blocks * P;
-    long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
-    h->h_segs.clear();
-    h->h_cta_first.assign((size_t)grid + 1, 0);
-    h->h_blk_first.assign((size_t)n_blocks + 1, 0);
-    for (long long c = 0; c < grid; ++c) {
-        long long f = c * F / grid;
-        const long long hi = (c + 1) * F / grid;
-        h->h_cta_first[c] = (int)h->h_segs.size();
-        while (f < hi) {
-            fx::fused4096::Segment sg;
-            sg.block = (int)(f / P);
-            sg.f0 = (int)(f % P);
-            sg.nf = (int)std::min<long long>(P - sg.f0, hi - f);
-            sg.pad = 0;
-            if (sg.f0 == 0) h->h_blk_first[sg.block] = (int)h->h_segs.size();
-            h->h_segs.push_back(sg);
-            f += sg.nf;
+    fx_handle::PlanSlot *slot = nullptr;
+    for (auto &pl : h->plans)
+        if (pl.units == n_blocks && pl.P == P) slot = &pl;
+    if (!slot) {
+        slot = &h->plans[0];
+        for (auto &pl : h->plans)
+            if (pl.last_use < slot->last_use) slot = &pl;
+        const long long Psf = (P + (1ll << h->logF) - 1) >> h->logF;      // the kernel walks super-frames of 2^logF frames
+        const long long F = n_blocks * Psf;
+        const long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
+        const size_t max_segs = (size_t)n_blocks + (size_t)grid;
+        const size_t n_int_max = max_segs * 4 + (size_t)grid + 1 + (size_t)n_blocks + 1;
+        if (n_int_max > h->plan_cap)
+            return fail(h, FX_ERR_INVALID, "segment plan exceeds the capacity sized from max_blocks in fx_create");
+        // the slot's pinned buffer may still be the source of its previous upload
+        if (slot->upload_recorded) FX_CUDA(h, cudaEventSynchronize(slot->uploaded));
+        int *flat = slot->h_pin;
+        fx::fused4096::Segment *segs = reinterpret_cast<fx::fused4096::Segment *>(flat);
+        size_t ns = 0;
+        std::vector<int> cta_first((size_t)grid + 1, 0), blk_first((size_t)n_blocks + 1, 0);
+        for (long long c = 0; c < grid; ++c) {
+            long long f = c * F / grid;
+            const long long hi = (c + 1) * F / grid;
+            cta_first[c] = (int)ns;
+            while (f < hi) {
+                fx::fused4096::Segment sg;
+                sg.block = (int)(f / Psf);
+                sg.f0 = (int)(f % Psf);
+                sg.nf = (int)std::min<long long>(Psf - sg.f0, hi - f);
+                sg.pad = 0;
+                if (sg.f0 == 0) blk_first[sg.block] = (int)ns;
+                segs[ns++] = sg;
+                f += sg.nf;
+            }
         }
+        cta_first[grid] = (int)ns;
+        blk_first[n_blocks] = (int)ns;
+        slot->n_segs = ns;
+        slot->off_cta = ns * 4;
+        memcpy(flat + slot->off_cta, cta_first.data(), cta_first.size() * sizeof(int));
+        slot->off_blk = slot->off_cta + cta_first.size();
+        memcpy(flat + slot->off_blk, blk_first.data(), blk_first.size() * sizeof(int));
+        const size_t n_int = slot->off_blk + blk_first.size();
+        slot->grid = (int)grid;
+        slot->units = n_blocks;
+        slot->P = P;
+        // stream-ordered: kernels already queued with this slot's old plan finish before the copy lands
+        FX_CUDA(h, cudaMemcpyAsync(slot->d_plan, flat, n_int * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        FX_CUDA(h, cudaEventRecord(slot->uploaded, h->stream));
+        slot->upload_recorded = true;
     }
-    h->h_cta_first[grid] = (int)h->h_segs.size();
-    h->h_blk_first[n_blocks] = (int)h->h_segs.size();
-    h->plan_grid = (int)grid;
-    const size_t n_int = h->h_segs.size() * 4 + h->h_cta_first.size() + h->h_blk_first.size();
-    if (n_int > h->segs_cap) {
-        if (h->d_plan) cudaFree(h->d_plan);
-        h->d_plan = nullptr;
-        h->segs_cap = 0;
-        FX_CUDA(h, cudaMalloc(&h->d_plan, n_int * sizeof(int)));
-        h->segs_cap = n_int;
-    }
-    std::vector<int> flat(n_int);
-    memcpy(flat.data(), h->h_segs.data(), h->h_segs.size() * sizeof(fx::fused4096::Segment));
-    size_t off = h->h_segs.size() * 4;
-    h->off_cta = off;
-    memcpy(flat.data() + off, h->h_cta_first.data(), h->h_cta_first.size() * sizeof(int));
-    off += h->h_cta_first.size();
-    h->off_blk = off;
-    memcpy(flat.data() + off, h->h_blk_first.data(), h->h_blk_first.size() * sizeof(int));
-    // synchronous copy: the host vectors may be rebuilt by the next call before an async copy is consumed
-    FX_CUDA(h, cudaStreamSynchronize(h->stream));
-    FX_CUDA(h, cudaMemcpy(h->d_plan, flat.data(), n_int * sizeof(int), cudaMemcpyHostToDevice));
-    h->planned_blocks = n_blocks;
-    h->planned_P = planned_P;
-    return ensure_parts(h, h->h_segs.size(), h->planning_big ? (size_t)fx::fused4096::N : 0);
+    slot->last_use = ++h->plan_clock;
+    h->d_plan = slot->d_plan;
+    h->off_cta = slot->off_cta;
+    h->off_blk = slot->off_blk;
+    h->n_segs = slot->n_segs;
+    h->plan_grid = slot->grid;
+    return ensure_parts(h, slot->n_segs, h->planning_big ? (size_t)fx::fused4096::N : 0);
 }
 
 // Options of one pass: reference semantics (independent blocks) or one streaming span.
@@ -254,16 +296,32 @@ struct PassOpts {
     const uint8_t *halo0 = nullptr, *halo1 = nullptr;   // streaming: the T-1 frames before the span (raw bytes)
     const unsigned long long *h_sums = nullptr;         // streaming: recording-wide byte sums (host), or NULL
     long long mean_count = 0;                            // samples h_sums were taken over
+    bool autos = true;                                   // accumulate |F0|^2, |F1|^2 (part_a) as well
 };
+
+// Where the float64 sums of a call go: local accumulators (+=), or -- reduce_root >= 0 -- through the
+// mailboxes of fx_comm.cuh into the root's flat accumulator buffer [acc_x 2N | a0 N | a1 N | frames 1].
+struct AccSink {
+    double *x = nullptr, *a0 = nullptr, *a1 = nullptr, *frames = nullptr;
+    int reduce_root = -1;
+    double *flat = nullptr;          // root only
+    bool any() const { return x != nullptr || reduce_root >= 0; }
+};
+
+__global__ void place_sums_kernel(unsigned long long *dst, unsigned long long s0, unsigned long long s1,
+                                  unsigned long long s2, unsigned long long s3) {
+    dst[0] = s0; dst[1] = s1; dst[2] = s2; dst[3] = s3;
+}
 
 int prepare_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o) {
     if (!o.h_sums) return launch_sums(h, d_iq0, d_iq1, o.units, o.S);
-    // recording-wide sums supplied by the caller (all-reduced across ranks): just place them
+    // recording-wide sums supplied by the caller (all-reduced across ranks): placed by a one-thread kernel
+    // whose arguments carry the values, so the call neither copies from the caller's memory nor synchronises
     const int set = (h->sums_idx ^= 1);
     h->d_sums = h->d_sums_set[set];
     if (h->sums_free_recorded[set]) FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_sums_free[set], 0));
-    FX_CUDA(h, cudaMemcpyAsync(h->d_sums, o.h_sums, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
-    FX_CUDA(h, cudaStreamSynchronize(h->stream));        // h_sums is the caller's stack/array
+    place_sums_kernel<<<1, 1, 0, h->stream>>>(h->d_sums, o.h_sums[0], o.h_sums[1], o.h_sums[2], o.h_sums[3]);
+    FX_LAUNCH_CHECK(h, "place_sums");
     return FX_OK;
 }
 
@@ -278,7 +336,7 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     prm.taps = h->d_taps4; prm.twA = h->d_twA; prm.twB = h->d_twB; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
     prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
     prm.part_x = h->d_part_x; prm.part_a = h->d_part_a;
-    prm.S = o.S; prm.n_segs = (int)h->h_segs.size(); prm.dc_remove = h->cfg.dc_remove;
+    prm.S = o.S; prm.n_segs = (int)h->n_segs; prm.dc_remove = h->cfg.dc_remove;
     prm.mean_count = o.mean_count > 0 ? o.mean_count : o.S;
     prm.halo0 = prm.halo1 = nullptr;
     if (o.halo0) {
@@ -289,7 +347,6 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
         const size_t halo_bytes = (size_t)(fx::fused4096::T - 1) * h->cfg.nbins * 2;
         const uint8_t *src[2] = {o.halo0, o.halo1};
         for (int c = 0; c < 2; ++c) {
-            if (!h->d_halo_pad[c]) FX_CUDA(h, cudaMalloc(&h->d_halo_pad[c], 3 * (size_t)fx::fused4096::FRAME_BYTES));
             FX_CUDA(h, cudaMemsetAsync(h->d_halo_pad[c], 128, pad_bytes, h->stream));
             FX_CUDA(h, cudaMemcpyAsync(h->d_halo_pad[c] + pad_bytes - halo_bytes, src[c], halo_bytes,
                                        cudaMemcpyDeviceToDevice, h->stream));
@@ -305,13 +362,17 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
     if (h->staggered) {
         using namespace fx::fused4096;
         const size_t smem = sizeof(SmemS);
+#define FX_STAG(LF)                                                                    \
+    if (o.autos) fused_kernel_stag<LF, true><<<grid, NT, smem, h->stream>>>(prm);      \
+    else fused_kernel_stag<LF, false><<<grid, NT, smem, h->stream>>>(prm)
         switch (h->logF) {
-            case 0: fused_kernel_stag<0><<<grid, NT, smem, h->stream>>>(prm); break;
-            case 1: fused_kernel_stag<1><<<grid, NT, smem, h->stream>>>(prm); break;
-            case 2: fused_kernel_stag<2><<<grid, NT, smem, h->stream>>>(prm); break;
-            case 3: fused_kernel_stag<3><<<grid, NT, smem, h->stream>>>(prm); break;
-            default: fused_kernel_stag<4><<<grid, NT, smem, h->stream>>>(prm); break;
+            case 0: FX_STAG(0); break;
+            case 1: FX_STAG(1); break;
+            case 2: FX_STAG(2); break;
+            case 3: FX_STAG(3); break;
+            default: FX_STAG(4); break;
         }
+#undef FX_STAG
     } else
         fx::fused4096::fused_kernel<<<grid, fx::fused4096::NT, sizeof(fx::fused4096::Smem), h->stream>>>(prm);
     FX_LAUNCH_CHECK(h, "fused4096");
@@ -330,13 +391,121 @@ size_t z_budget() {
     return size_t(1) << 26;
 }
 
+// ---- cross-GPU reduce through the mailboxes (fx_comm.cuh) ---------------------------------------------
+char *comm_base(fx_handle *h, int r) { return r == h->comm.rank ? h->comm.local : h->comm.peer[r]; }
+
+// next epoch: where this rank's contribution goes in the root's mailbox
+int comm_begin(fx_handle *h, int root, fx::comm::PushTarget &t) {
+    auto &c = h->comm;
+    if (!c.attached) return fail(h, FX_ERR_STATE, "fx_comm_attach must be called first");
+    if (root < 0 || root >= c.world) return fail(h, FX_ERR_INVALID, "reduce root out of range");
+    const unsigned int e = ++c.epoch;
+    const size_t par = e & 1u;
+    char *base = comm_base(h, root);
+    t.slot = base + c.off_slots + (par * c.world + c.rank) * c.slot_bytes;
+    t.flag = reinterpret_cast<unsigned int *>(base + c.off_flags) + (par * c.world + c.rank) * c.ctas;
+    t.done = reinterpret_cast<const unsigned int *>(base + c.off_done);
+    t.err = reinterpret_cast<unsigned int *>(c.local);
+    t.epoch = e;
+    t.timeout_cycles = c.timeout_cycles;
+    return FX_OK;
+}
+// root: fold the world slots of the current epoch into dst, on the fold stream, after this rank's own push
+template <typename T>
+int comm_end(fx_handle *h, int root, T *dst, size_t n, int accumulate) {
+    auto &c = h->comm;
+    if (root != c.rank) return FX_OK;
+    if (!dst) return fail(h, FX_ERR_INVALID, "the reduce root needs a destination buffer");
+    FX_CUDA(h, cudaEventRecord(c.ev_push, h->stream));
+    FX_CUDA(h, cudaStreamWaitEvent(c.stream_fold, c.ev_push, 0));
+    const size_t par = c.epoch & 1u;
+    fx::comm::fold_kernel<T><<<c.ctas, fx::comm::kThreads, 0, c.stream_fold>>>(
+        dst, n, c.local + c.off_slots + par * c.world * c.slot_bytes, c.slot_bytes,
+        reinterpret_cast<const unsigned int *>(c.local + c.off_flags) + par * c.world * c.ctas, c.ctas, c.world,
+        reinterpret_cast<unsigned int *>(c.local + c.off_done), reinterpret_cast<unsigned int *>(c.local), c.epoch,
+        accumulate, c.timeout_cycles);
+    FX_LAUNCH_CHECK(h, "comm_fold");
+    FX_CUDA(h, cudaEventRecord(c.ev_fold, c.stream_fold));
+    c.fold_pending = true;
+    return FX_OK;
+}
+template <typename T>
+int comm_reduce(fx_handle *h, T *d_buf, size_t n, int root) {
+    auto &c = h->comm;
+    if (n * sizeof(T) > c.slot_bytes) return fail(h, FX_ERR_INVALID, "buffer larger than the mailbox slots of fx_comm_export");
+    fx::comm::PushTarget t;
+    int rc = comm_begin(h, root, t);
+    if (rc) return rc;
+    fx::comm::push_kernel<T><<<c.ctas, fx::comm::kThreads, 0, h->stream>>>(d_buf, n, t);
+    FX_LAUNCH_CHECK(h, "comm_push");
+    rc = comm_end<T>(h, root, d_buf, n, 0);
+    if (rc) return rc;
+    if (c.fold_pending) FX_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_fold, 0));   // in place: order later users of d_buf
+    return FX_OK;
+}
+
+// stage 2 of an integration: fold the G group sums of scratch into the sink.  `staged` (paths that run
+// several stage-2 passes per call) adds into the handle's local staging accumulators instead; sink_flush
+// then pushes them once.
+int launch_stage2(fx_handle *h, int NB, int G, double frames, const AccSink &sink, bool staged) {
+    if (sink.reduce_root < 0 || staged) {
+        double *x = sink.x, *a0 = sink.a0, *a1 = sink.a1, *fr = sink.frames;
+        if (sink.reduce_root >= 0) {
+            double *l = h->comm.d_acc_local;
+            x = l; a0 = l + 2 * (size_t)NB; a1 = l + 3 * (size_t)NB; fr = l + 4 * (size_t)NB;
+        }
+        fx::generic::integrate_stage2_kernel<<<(4 * NB + 255) / 256, 256, 0, h->stream>>>(h->d_int_scratch, NB, G, frames,
+                                                                                      x, a0, a1, fr);
+        FX_LAUNCH_CHECK(h, "integrate_stage2");
+        return FX_OK;
+    }
+    fx::comm::PushTarget t;
+    int rc = comm_begin(h, sink.reduce_root, t);
+    if (rc) return rc;
+    fx::comm::integrate_push_kernel<<<h->comm.ctas, fx::comm::kThreads, 0, h->stream>>>(h->d_int_scratch, NB, G, frames, t);
+    FX_LAUNCH_CHECK(h, "integrate_push");
+    return comm_end<double>(h, sink.reduce_root, sink.flat, 4 * (size_t)NB + 1, 1);
+}
+int sink_begin(fx_handle *h, int NB, const AccSink &sink, bool staged) {
+    if (sink.reduce_root < 0) return FX_OK;
+    if (!h->comm.attached) return fail(h, FX_ERR_STATE, "fx_comm_attach must be called first");
+    if ((4 * (size_t)NB + 1) * sizeof(double) > h->comm.slot_bytes)
+        return fail(h, FX_ERR_INVALID, "mailbox slots are smaller than the accumulators");
+    if (staged) FX_CUDA(h, cudaMemsetAsync(h->comm.d_acc_local, 0, (4 * (size_t)NB + 1) * sizeof(double), h->stream));
+    return FX_OK;
+}
+int sink_flush(fx_handle *h, int NB, const AccSink &sink, bool staged) {
+    if (sink.reduce_root < 0 || !staged) return FX_OK;
+    const size_t n = 4 * (size_t)NB + 1;
+    fx::comm::PushTarget t;
+    int rc = comm_begin(h, sink.reduce_root, t);
+    if (rc) return rc;
+    fx::comm::push_kernel<double><<<h->comm.ctas, fx::comm::kThreads, 0, h->stream>>>(h->comm.d_acc_local, n, t);
+    FX_LAUNCH_CHECK(h, "comm_push");
+    return comm_end<double>(h, sink.reduce_root, sink.flat, n, 1);
+}
+
+int launch_tail(fx_handle *h, const fx::bigfft::TailParams &prm, bool autos) {
+    using namespace fx::bigfft;
+    EventPair ep{};
+    int rc = begin_timed(h, ep);
+    if (rc) return rc;
+    if (autos) tail_kernel<true><<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
+    else tail_kernel<false><<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
+    FX_LAUNCH_CHECK(h, "bigfft_tail");
+    return end_timed(h, ep);
+}
+
 // nbins = G*4096: head kernel -> Z -> tail kernel -> rows, a chunk of blocks at a time (Z <= 1 GiB)
 int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
-            float *d_auto0, float *d_auto1, double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+            float *d_auto0, float *d_auto1, const AccSink &sink) {
     using namespace fx::bigfft;
     const int NB = h->cfg.nbins, G = 1 << h->logG, P = h->P;
     const long long S = h->cfg.num_samp;
+    const bool autos = d_auto0 || d_auto1 || sink.any();
     int rc = launch_sums(h, d_iq0, d_iq1, n_blocks, S);
+    if (rc) return rc;
+    rc = sink_begin(h, NB, sink, true);
     if (rc) return rc;
     const size_t per_block = (size_t)P * NB;                              // float4 elements of Z
     long long chunk = (long long)std::max<size_t>(1, z_budget() / per_block);
@@ -368,22 +537,15 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
         prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
         prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = P;
-        EventPair ep{};
-        rc = begin_timed(h, ep);
+        rc = launch_tail(h, prm, autos);
         if (rc) return rc;
-        tail_kernel<<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
-        FX_LAUNCH_CHECK(h, "bigfft_tail");
-        rc = end_timed(h, ep);
-        if (rc) return rc;
-        if (d_acc_x) {
-            if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)NB));
+        if (sink.any()) {
             const int groups = (int)std::max<long long>(1, std::min<long long>(64, nb));
             integrate_kernel<<<dim3((NB + 255) / 256, groups), 256, 0, h->stream>>>(
                 h->d_part_x, h->d_part_a, NB, h->logG, h->d_plan + h->off_blk, (int)nb, h->d_int_scratch);
             FX_LAUNCH_CHECK(h, "bigfft_integrate");
-            fx::generic::integrate_stage2_kernel<<<(4 * NB + 255) / 256, 256, 0, h->stream>>>(
-                h->d_int_scratch, NB, groups, (double)nb * (double)P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-            FX_LAUNCH_CHECK(h, "integrate_stage2");
+            rc = launch_stage2(h, NB, groups, (double)nb * (double)P, sink, true);
+            if (rc) return rc;
         }
         if (!d_xspec) continue;
         dim3 fg((NB + 255) / 256, (unsigned)nb);
@@ -393,17 +555,20 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
                                                    d_auto0 ? d_auto0 + b0 * NB : nullptr, d_auto1 ? d_auto1 + b0 * NB : nullptr);
         FX_LAUNCH_CHECK(h, "bigfft_finalize");
     }
+    rc = sink_flush(h, NB, sink, true);
+    if (rc) return rc;
     return release_sums(h);
 }
 
 // streaming-history span at nbins = G*4096: ONE unit of o.P frames (recording-wide mean, halo frames),
 // walked in chunks of frames so that Z stays under 1 GiB; only the float64 accumulators are produced
-int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o, double *d_acc_x,
-                 double *d_acc_a0, double *d_acc_a1, double *d_frames) {
+int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const PassOpts &o, const AccSink &sink) {
     using namespace fx::bigfft;
     const int NB = h->cfg.nbins, G = 1 << h->logG;
     const long long P = o.P;
     int rc = prepare_sums(h, d_iq0, d_iq1, o);
+    if (rc) return rc;
+    rc = sink_begin(h, NB, sink, true);
     if (rc) return rc;
     const long long mean_count = o.mean_count > 0 ? o.mean_count : o.S;
     long long fc = ((long long)z_budget() / NB / kHeadFrames) * kHeadFrames;             // frames per chunk
@@ -416,7 +581,6 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
         FX_CUDA(h, cudaMalloc(&h->d_z, need * sizeof(float4)));
         h->z_cap = need;
     }
-    if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)NB));
     for (long long ib = 0; ib < P; ib += fc) {
         const int n = (int)std::min<long long>(fc, P - ib);
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((n + kHeadFrames - 1) / kHeadFrames), 1);
@@ -437,20 +601,16 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
         prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
         prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
         prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = n;
-        EventPair ep{};
-        rc = begin_timed(h, ep);
-        if (rc) return rc;
-        tail_kernel<<<h->plan_grid, fx::fused4096::NT, sizeof(SmemT), h->stream>>>(prm);
-        FX_LAUNCH_CHECK(h, "bigfft_tail");
-        rc = end_timed(h, ep);
+        rc = launch_tail(h, prm, true);
         if (rc) return rc;
         integrate_kernel<<<dim3((NB + 255) / 256, 1), 256, 0, h->stream>>>(h->d_part_x, h->d_part_a, NB, h->logG,
                                                                            h->d_plan + h->off_blk, 1, h->d_int_scratch);
         FX_LAUNCH_CHECK(h, "bigfft_integrate");
-        fx::generic::integrate_stage2_kernel<<<(4 * NB + 255) / 256, 256, 0, h->stream>>>(
-            h->d_int_scratch, NB, 1, (double)n, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-        FX_LAUNCH_CHECK(h, "integrate_stage2");
+        rc = launch_stage2(h, NB, 1, (double)n, sink, true);
+        if (rc) return rc;
     }
+    rc = sink_flush(h, NB, sink, true);
+    if (rc) return rc;
     return release_sums(h);
 }
 
@@ -621,18 +781,19 @@ PassOpts block_opts(const fx_handle *h, long long n_blocks) {
 }
 
 int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, float *d_xspec,
-                   float *d_auto0, float *d_auto1, double *d_acc_x = nullptr, double *d_acc_a0 = nullptr,
-                   double *d_acc_a1 = nullptr, double *d_frames = nullptr, const PassOpts *span = nullptr) {
-    if (h->big && span && d_acc_x && !d_xspec && span->P <= 0x7fffffffll && (span->S & 1) == 0)
-        return run_big_span(h, d_iq0, d_iq1, *span, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+                   float *d_auto0, float *d_auto1, const AccSink &sink = AccSink(), const PassOpts *span = nullptr) {
+    if (h->big && span && sink.any() && !d_xspec && span->P <= 0x7fffffffll && (span->S & 1) == 0)
+        return run_big_span(h, d_iq0, d_iq1, *span, sink);
     if (h->big && !span && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
-        return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-    const PassOpts o = span ? *span : block_opts(h, n_blocks);
-    int rc = run_parts(h, d_iq0, d_iq1, o);
-    if (rc) return rc;
+        return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, sink);
+    PassOpts o = span ? *span : block_opts(h, n_blocks);
+    o.autos = d_auto0 || d_auto1 || sink.any();
     const int N = h->cfg.nbins;
-    if (d_acc_x) {
-        if (!h->d_int_scratch) FX_CUDA(h, cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)N));
+    int rc = sink_begin(h, N, sink, false);
+    if (rc) return rc;
+    rc = run_parts(h, d_iq0, d_iq1, o);
+    if (rc) return rc;
+    if (sink.any()) {
         int G;
         if (d_xspec) {
             // rows and accumulators from ONE pass over the partial sums
@@ -643,16 +804,13 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
                 d_auto1, h->d_int_scratch);
             FX_LAUNCH_CHECK(h, "finalize_integrate");
         } else {
-            const int n_segs = h->parts_per_block ? (int)o.units : (int)h->h_segs.size();
+            const int n_segs = h->parts_per_block ? (int)o.units : (int)h->n_segs;
             G = std::max(1, std::min(64, n_segs / 4));
             fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
                 h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
             FX_LAUNCH_CHECK(h, "integrate_stage1");
         }
-        fx::generic::integrate_stage2_kernel<<<(4 * N + 255) / 256, 256, 0, h->stream>>>(
-            h->d_int_scratch, N, G, (double)o.units * (double)o.P, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
-        FX_LAUNCH_CHECK(h, "integrate_stage2");
-        if (d_xspec) return FX_OK;
+        return launch_stage2(h, N, G, (double)o.units * (double)o.P, sink, false);
     }
     if (!d_xspec) return FX_OK;
     dim3 grid((N + 255) / 256, 1);
@@ -746,6 +904,47 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     return FX_OK;
 }
 
+struct CommToken {                 // what fx_comm_export hands out (FX_COMM_TOKEN_BYTES = 128)
+    cudaIpcMemHandle_t ipc;        // 64 bytes
+    unsigned long long ptr, bytes, slot_bytes;
+    int pid, device, world, ctas;
+    unsigned int magic;
+};
+static_assert(sizeof(CommToken) <= FX_COMM_TOKEN_BYTES, "token does not fit");
+constexpr unsigned int kTokenMagic = 0x46584d42u;   // "FXMB"
+
+void comm_release(fx_handle *h) {
+    auto &c = h->comm;
+    for (int r = 0; r < fx::comm::kMaxWorld; ++r) {
+        if (c.peer[r] && c.peer_ipc[r]) cudaIpcCloseMemHandle(c.peer[r]);
+        c.peer[r] = nullptr;
+        c.peer_ipc[r] = false;
+    }
+    if (c.local) cudaFree(c.local);
+    if (c.d_acc_local) cudaFree(c.d_acc_local);
+    c.local = nullptr;
+    c.d_acc_local = nullptr;
+    if (c.ev_push) cudaEventDestroy(c.ev_push);
+    if (c.ev_fold) cudaEventDestroy(c.ev_fold);
+    if (c.stream_fold) cudaStreamDestroy(c.stream_fold);
+    c.ev_push = c.ev_fold = nullptr;
+    c.stream_fold = nullptr;
+    c.exported = c.attached = c.fold_pending = false;
+}
+
+// error word of the mailbox (set by a spin that hit its deadline); called with all streams idle
+int comm_check(fx_handle *h) {
+    auto &c = h->comm;
+    if (!c.exported) return FX_OK;
+    unsigned int e = 0;
+    FX_CUDA(h, cudaMemcpy(&e, c.local, sizeof(e), cudaMemcpyDeviceToHost));
+    if (!e) return FX_OK;
+    FX_CUDA(h, cudaMemset(c.local, 0, sizeof(e)));
+    return fail(h, FX_ERR_COMM, std::string("cross-GPU reduce timed out waiting for ") +
+                                    ((e & fx::comm::kErrTimeoutFold) ? "a peer's contribution" : "the root's acknowledgement") +
+                                    " (are all ranks making the same sequence of reduce calls?)");
+}
+
 }  // namespace
 
 extern "C" {
@@ -818,12 +1017,33 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_sums_free[i], cudaEventDisableTiming));
     }
     h->d_sums = h->d_sums_set[0];
+    {   // everything the hot calls need is sized here from max_blocks (no allocation or sync in fx_process):
+        // plan slots (device + pinned staging), partial sums, integrate scratch, halo staging, Z
+        const int G = h->big ? (1 << h->logG) : 1;
+        const size_t max_units = std::max<size_t>(std::min<size_t>((size_t)cfg->max_blocks * G, 65535), (size_t)G);
+        const size_t max_segs = std::max<size_t>(max_units, (size_t)cfg->max_blocks) + (size_t)h->num_sms;
+        h->plan_cap = max_segs * 4 + (size_t)h->num_sms + 1 + std::max<size_t>(max_units, (size_t)cfg->max_blocks) + 1;
+        for (auto &pl : h->plans) {
+            CREATE_CUDA(cudaMalloc(&pl.d_plan, h->plan_cap * sizeof(int)));
+            CREATE_CUDA(cudaHostAlloc(&pl.h_pin, h->plan_cap * sizeof(int), cudaHostAllocDefault));
+            CREATE_CUDA(cudaEventCreateWithFlags(&pl.uploaded, cudaEventDisableTiming));
+        }
+        // partial sums: one slice of min(nbins, 4096) bins per segment; pre-sized up to 256 MiB per buffer
+        // (larger calls grow them on first use)
+        const size_t bins = std::min<size_t>((size_t)cfg->nbins, (size_t)fx::fused4096::N);
+        const size_t want = std::min<size_t>(max_segs * bins, size_t(1) << 25);
+        CREATE_CUDA(cudaMalloc(&h->d_part_x, want * sizeof(float2)));
+        CREATE_CUDA(cudaMalloc(&h->d_part_a, want * sizeof(float2)));
+        h->part_cap = want;
+        CREATE_CUDA(cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)cfg->nbins));
+    }
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      3 * 4096 * (int)sizeof(float2)));
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::stockham_radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (2 * 256 * (fx::generic::kPassJ + 1) + 256) * (int)sizeof(float2)));
     if (h->fused || h->big) {
         CREATE_CUDA(cudaMalloc(&h->d_taps4, fx::fused4096::N * sizeof(float4)));
+        for (int c = 0; c < 2; ++c) CREATE_CUDA(cudaMalloc(&h->d_halo_pad[c], 3 * (size_t)fx::fused4096::FRAME_BYTES));
         CREATE_CUDA(cudaMalloc(&h->d_twA, 16 * 256 * sizeof(float2)));
         CREATE_CUDA(cudaMalloc(&h->d_twB, 16 * 16 * sizeof(float2)));
         std::vector<float2> twA(16 * 256), twB(16 * 16);
@@ -871,10 +1091,13 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                          (int)sizeof(fx::fused4096::Smem)));
         {
             using namespace fx::fused4096;
-            const void *ks[5] = {(const void *)fused_kernel_stag<0>, (const void *)fused_kernel_stag<1>,
-                                 (const void *)fused_kernel_stag<2>, (const void *)fused_kernel_stag<3>,
-                                 (const void *)fused_kernel_stag<4>};
-            CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+            const void *ks[5][2] = {{(const void *)fused_kernel_stag<0, false>, (const void *)fused_kernel_stag<0, true>},
+                                    {(const void *)fused_kernel_stag<1, false>, (const void *)fused_kernel_stag<1, true>},
+                                    {(const void *)fused_kernel_stag<2, false>, (const void *)fused_kernel_stag<2, true>},
+                                    {(const void *)fused_kernel_stag<3, false>, (const void *)fused_kernel_stag<3, true>},
+                                    {(const void *)fused_kernel_stag<4, false>, (const void *)fused_kernel_stag<4, true>}};
+            for (int a = 0; a < 2; ++a)
+                CREATE_CUDA(cudaFuncSetAttribute(ks[h->logF][a], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         }
         if (h->big) {
             const int G = 1 << h->logG, NB = cfg->nbins;
@@ -889,8 +1112,16 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         }
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 << 4));
-        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::bigfft::SmemT)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(fx::bigfft::SmemT)));
+        if (h->big) {    // the intermediate Z of the head/tail pair: at most 1 GiB, or what max_blocks blocks need
+            const size_t per_block = (size_t)h->P * cfg->nbins;
+            const size_t want = std::min<size_t>(z_budget(), per_block * (size_t)cfg->max_blocks);
+            CREATE_CUDA(cudaMalloc(&h->d_z, std::max<size_t>(want, (size_t)fx::bigfft::kHeadFrames * cfg->nbins) * sizeof(float4)));
+            h->z_cap = std::max<size_t>(want, (size_t)fx::bigfft::kHeadFrames * cfg->nbins);
+        }
         // the lock-step cross-check kernel exists for 4096 bins only
         h->staggered = !(cfg->flags & FX_FLAG_LOCKSTEP_KERNEL) || h->logF != 0;
     }
@@ -905,13 +1136,20 @@ int fx_destroy(fx_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
+    if (h->comm.stream_fold) cudaStreamSynchronize(h->comm.stream_fold);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_plan, h->d_int_scratch, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_int_scratch, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &pl : h->plans) {
+        if (pl.d_plan) cudaFree(pl.d_plan);
+        if (pl.h_pin) cudaFreeHost(pl.h_pin);
+        if (pl.uploaded) cudaEventDestroy(pl.uploaded);
+    }
+    comm_release(h);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -935,7 +1173,9 @@ int fx_sync(fx_handle *h) {
     FX_CUDA(h, cudaStreamSynchronize(h->stream_aux));
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     FX_CUDA(h, cudaStreamSynchronize(h->stream_copy));
-    return FX_OK;
+    if (h->comm.stream_fold) FX_CUDA(h, cudaStreamSynchronize(h->comm.stream_fold));
+    h->comm.fold_pending = false;
+    return comm_check(h);
 }
 
 int fx_uses_fused(const fx_handle *h) { return h && h->fused ? 1 : 0; }
@@ -999,7 +1239,9 @@ int fx_process_acc(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int
     if (rc) return rc;
     if (!d_acc_x || !d_acc_a0 || !d_acc_a1) return fail(h, FX_ERR_INVALID, "null accumulator pointer");
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
-    return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, d_acc_x, d_acc_a0, d_acc_a1, d_frames);
+    AccSink sink;
+    sink.x = d_acc_x; sink.a0 = d_acc_a0; sink.a1 = d_acc_a1; sink.frames = d_frames;
+    return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, sink);
 }
 
 int fx_span_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, uint64_t h_sums[4]) {
@@ -1038,7 +1280,9 @@ int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1
         o.h_sums = sums_copy;
         o.mean_count = total_samp;
     }
-    return process_device(h, d_iq0, d_iq1, 1, nullptr, nullptr, nullptr, d_acc_x, d_acc_a0, d_acc_a1, d_frames, &o);
+    AccSink sink;
+    sink.x = d_acc_x; sink.a0 = d_acc_a0; sink.a1 = d_acc_a1; sink.frames = d_frames;
+    return process_device(h, d_iq0, d_iq1, 1, nullptr, nullptr, nullptr, sink, &o);
 }
 
 int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,
@@ -1202,5 +1446,153 @@ int fx_dominant_kernel_time(fx_handle *h, double *ms_total, int64_t *launches) {
 }
 void *fx_stream(fx_handle *h) { return h ? (void *)h->stream : nullptr; }
 void *fx_stream_aux(fx_handle *h) { return h ? (void *)h->stream_aux : nullptr; }
+
+/* ---- cross-GPU reduce (fx_comm.cuh) ------------------------------------------------------------------ */
+int fx_comm_export(fx_handle *h, int world, size_t slot_bytes, void *h_token) {
+    if (!h || !h_token) return FX_ERR_INVALID;
+    if (world < 1 || world > fx::comm::kMaxWorld) return fail(h, FX_ERR_INVALID, "world must be in [1, 16]");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = fx_sync(h);
+    if (rc) return rc;
+    comm_release(h);
+    auto &c = h->comm;
+    const size_t acc_bytes = (4 * (size_t)h->cfg.nbins + 1) * sizeof(double);
+    c.slot_bytes = (std::max(slot_bytes, acc_bytes) + 255) / 256 * 256;
+    c.world = world;
+    c.ctas = (int)((4 * (size_t)h->cfg.nbins + 1 + fx::comm::kThreads - 1) / fx::comm::kThreads);
+    c.off_done = 256;
+    c.off_flags = c.off_done + ((size_t)c.ctas * 4 + 255) / 256 * 256;
+    c.off_slots = c.off_flags + ((size_t)2 * world * c.ctas * 4 + 255) / 256 * 256;
+    c.local_bytes = c.off_slots + (size_t)2 * world * c.slot_bytes;
+    FX_CUDA(h, cudaMalloc(&c.local, c.local_bytes));
+    FX_CUDA(h, cudaMemset(c.local, 0, c.local_bytes));
+    FX_CUDA(h, cudaMalloc(&c.d_acc_local, acc_bytes));
+    FX_CUDA(h, cudaStreamCreateWithFlags(&c.stream_fold, cudaStreamNonBlocking));
+    FX_CUDA(h, cudaEventCreateWithFlags(&c.ev_push, cudaEventDisableTiming));
+    FX_CUDA(h, cudaEventCreateWithFlags(&c.ev_fold, cudaEventDisableTiming));
+    FX_CUDA(h, cudaDeviceSynchronize());
+    if (const char *e = getenv("EFFEX_FX_COMM_TIMEOUT_MS")) {
+        const double ms = atof(e);
+        if (ms > 0) c.timeout_cycles = (long long)(ms * 1.9e6);
+    }
+    CommToken tok;
+    memset(&tok, 0, sizeof(tok));
+    FX_CUDA(h, cudaIpcGetMemHandle(&tok.ipc, c.local));
+    tok.ptr = (unsigned long long)(uintptr_t)c.local;
+    tok.bytes = c.local_bytes;
+    tok.slot_bytes = c.slot_bytes;
+    tok.pid = (int)getpid();
+    tok.device = h->cfg.device;
+    tok.world = world;
+    tok.ctas = c.ctas;
+    tok.magic = kTokenMagic;
+    memset(h_token, 0, FX_COMM_TOKEN_BYTES);
+    memcpy(h_token, &tok, sizeof(tok));
+    c.exported = true;
+    c.epoch = 0;
+    return FX_OK;
+}
+
+int fx_comm_attach(fx_handle *h, int rank, int world, const void *h_tokens) {
+    if (!h || !h_tokens) return FX_ERR_INVALID;
+    auto &c = h->comm;
+    if (!c.exported) return fail(h, FX_ERR_STATE, "fx_comm_export must be called first");
+    if (world != c.world || rank < 0 || rank >= world) return fail(h, FX_ERR_INVALID, "rank/world do not match fx_comm_export");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const char *toks = reinterpret_cast<const char *>(h_tokens);
+    for (int r = 0; r < world; ++r) {
+        CommToken tok;
+        memcpy(&tok, toks + (size_t)r * FX_COMM_TOKEN_BYTES, sizeof(tok));
+        if (tok.magic != kTokenMagic || tok.world != world || tok.ctas != c.ctas || tok.slot_bytes != c.slot_bytes ||
+            tok.bytes != c.local_bytes)
+            return fail(h, FX_ERR_INVALID, "token of rank " + std::to_string(r) + " does not match this handle's mailbox (same nbins, world and slot size on every rank?)");
+        if (r == rank) {
+            if (tok.ptr != (unsigned long long)(uintptr_t)c.local || tok.pid != (int)getpid())
+                return fail(h, FX_ERR_INVALID, "token[rank] is not this handle's own token");
+            continue;
+        }
+        if (tok.pid == (int)getpid()) {
+            // same process (one host thread driving several GPUs): the pointer is valid as it is
+            if (tok.device != h->cfg.device) {
+                int can = 0;
+                FX_CUDA(h, cudaDeviceCanAccessPeer(&can, h->cfg.device, tok.device));
+                if (!can) return fail(h, FX_ERR_COMM, "no peer access between devices " + std::to_string(h->cfg.device) + " and " + std::to_string(tok.device));
+                cudaError_t e = cudaDeviceEnablePeerAccess(tok.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(h, FX_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                (void)cudaGetLastError();
+            }
+            c.peer[r] = reinterpret_cast<char *>((uintptr_t)tok.ptr);
+            c.peer_ipc[r] = false;
+        } else {
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, tok.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(h, FX_ERR_COMM, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+            c.peer[r] = reinterpret_cast<char *>(p);
+            c.peer_ipc[r] = true;
+        }
+    }
+    c.rank = rank;
+    c.attached = true;
+    return FX_OK;
+}
+
+int fx_comm_fence(fx_handle *h) {
+    if (!h) return FX_ERR_INVALID;
+    if (h->comm.fold_pending) FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->comm.ev_fold, 0));
+    return FX_OK;
+}
+
+int fx_process_reduce(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, float *d_xspec,
+                      float *d_auto0, float *d_auto1, int root, double *d_acc_flat) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!h->comm.attached) return fail(h, FX_ERR_STATE, "fx_comm_attach must be called first");
+    if (root == h->comm.rank && !d_acc_flat) return fail(h, FX_ERR_INVALID, "the root needs d_acc_flat");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    AccSink sink;
+    sink.reduce_root = root;
+    sink.flat = d_acc_flat;
+    return process_device(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, sink);
+}
+
+int fx_integrate_stream_reduce(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                               const uint8_t *d_halo0, const uint8_t *d_halo1, const uint64_t *h_sums,
+                               int64_t total_samp, int root, double *d_acc_flat) {
+    int rc = check_process_args(h, d_iq0, d_iq1, n_blocks);
+    if (rc) return rc;
+    if (!h->comm.attached) return fail(h, FX_ERR_STATE, "fx_comm_attach must be called first");
+    if (root == h->comm.rank && !d_acc_flat) return fail(h, FX_ERR_INVALID, "the root needs d_acc_flat");
+    if ((d_halo0 == nullptr) != (d_halo1 == nullptr)) return fail(h, FX_ERR_INVALID, "give both halos or none");
+    if (h_sums && total_samp < 1) return fail(h, FX_ERR_INVALID, "total_samp must accompany h_sums");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    PassOpts o;
+    o.units = 1;
+    o.S = (long long)n_blocks * h->cfg.num_samp;
+    o.P = o.S / h->cfg.nbins;
+    o.halo0 = d_halo0; o.halo1 = d_halo1;
+    unsigned long long sums_copy[4];
+    if (h_sums) {
+        for (int i = 0; i < 4; ++i) sums_copy[i] = h_sums[i];
+        o.h_sums = sums_copy;
+        o.mean_count = total_samp;
+    }
+    AccSink sink;
+    sink.reduce_root = root;
+    sink.flat = d_acc_flat;
+    return process_device(h, d_iq0, d_iq1, 1, nullptr, nullptr, nullptr, sink, &o);
+}
+
+int fx_reduce_f64(fx_handle *h, double *d_buf, size_t n, int root) {
+    if (!h || !d_buf) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return comm_reduce<double>(h, d_buf, n, root);
+}
+int fx_reduce_f32(fx_handle *h, float *d_buf, size_t n, int root) {
+    if (!h || !d_buf) return FX_ERR_INVALID;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return comm_reduce<float>(h, d_buf, n, root);
+}
 
 }  // extern "C"

@@ -175,6 +175,7 @@ struct TailParams {
     int G, P;
 };
 
+template <bool AUTOS>
 __global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
     using namespace fused4096;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,11 +199,11 @@ __global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
         const Segment sg = prm.segs[seg];
         const int blk = sg.block / prm.G, k1 = sg.block % prm.G;
         const float4 *zseg = prm.z + (((long long)blk * prm.P + sg.f0) * prm.G + k1) * N;
-        float2 accx[16], acca[16];
+        float2 accx[16], acca[AUTOS ? 16 : 1];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             accx[j] = f2(0.f, 0.f);
-            acca[j] = f2(0.f, 0.f);
+            if (AUTOS) acca[j] = f2(0.f, 0.f);
         }
         C2 v[16];
 
@@ -277,7 +278,7 @@ __global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
                 const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
                 accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
                 accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
-                acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+                if (AUTOS) acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
             }
         };
 
@@ -302,7 +303,7 @@ __global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
                 const int idx = k1B + 16 * lo + 256 * perm16(jj);
                 const int sw = idx ^ ((idx >> 4) & 15);
                 sts_pair(&xs[sw], accx[jj]);
-                sts_pair(&xs[N + sw], acca[jj]);
+                if (AUTOS) sts_pair(&xs[N + sw], acca[jj]);
             }
             __syncthreads();
             float2 *px = prm.part_x + (long long)seg * N;
@@ -312,7 +313,7 @@ __global__ void __maxnreg__(FX_MAXNREG) tail_kernel(const TailParams prm) {
                 const int o = t + NT * q;
                 const int sw = o ^ ((o >> 4) & 15);
                 px[o] = xs[sw];
-                pa[o] = xs[N + sw];
+                if (AUTOS) pa[o] = xs[N + sw];
             }
             __syncthreads();
         }
@@ -334,10 +335,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float2 *__restrict_
     const int k1 = c & ((1 << logG) - 1), k2 = c >> logG;
     const int vb = (b << logG) + k1;
     float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+    const bool autos = auto0 || auto1;
     for (int s = vblk_first[vb]; s < vblk_first[vb + 1]; ++s) {
         const float2 x = part_x[(long long)s * N + k2];
-        const float2 a = part_a[(long long)s * N + k2];
-        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+        xr += x.x; xi += x.y;
+        if (autos) {
+            const float2 a = part_a[(long long)s * N + k2];
+            a0 += a.x; a1 += a.y;
+        }
     }
     xr *= inv_frames; xi *= inv_frames;
     const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);

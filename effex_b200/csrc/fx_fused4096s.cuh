@@ -147,7 +147,9 @@ __device__ __forceinline__ void dft_small(C2 *v) {
 #ifndef FX_MAXNREG
 #define FX_MAXNREG 232
 #endif
-template <int LOGF>
+// AUTOS = false drops the auto-power accumulators (32 registers, 32 FFMA2 per frame and thread) and the
+// part_a stores: fx_process without d_auto0/d_auto1 and without accumulators never reads them.
+template <int LOGF, bool AUTOS>
 __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
     constexpr int F = 1 << LOGF;        // frames per super-frame
     constexpr int RP = 16 >> LOGF;      // positions of one frame held by a thread = stage-A radix
@@ -262,11 +264,11 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
             }
         };
 
-        float2 accx[16], acca[16];
+        float2 accx[16], acca[AUTOS ? 16 : 1];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             accx[j] = f2(0.f, 0.f);
-            acca[j] = f2(0.f, 0.f);
+            if (AUTOS) acca[j] = f2(0.f, 0.f);
         }
         C2 v[16];
         // zero FIR state: a segment either starts a block (zero history is the reference's semantics)
@@ -409,7 +411,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
                     const float re0 = v[jj].r.x, re1 = v[jj].r.y, im0 = v[jj].i.x, im1 = v[jj].i.y;
                     accx[jj].x = fmaf(re0, re1, fmaf(im0, im1, accx[jj].x));
                     accx[jj].y = fmaf(im0, re1, fmaf(-re0, im1, accx[jj].y));
-                    acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
+                    if (AUTOS) acca[jj] = f2fma(v[jj].r, v[jj].r, f2fma(v[jj].i, v[jj].i, acca[jj]));
                 }
             }
         };
@@ -442,7 +444,7 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
                 const int idx = fslot * NL + (k1B & (RP - 1)) + RP * lo + 16 * RP * perm16(jj);
                 const int sw = idx ^ ((idx >> 4) & 15);
                 sts_pair(&xs[sw], accx[jj]);
-                sts_pair(&xs[N + sw], acca[jj]);
+                if (AUTOS) sts_pair(&xs[N + sw], acca[jj]);
             }
             __syncthreads();
             float2 *px = prm.part_x + (long long)seg * NL;
@@ -456,10 +458,10 @@ __global__ void __maxnreg__(FX_MAXNREG) fused_kernel_stag(const Params prm) {
                     const int idx = f * NL + o;
                     const int sw = idx ^ ((idx >> 4) & 15);
                     sx = f2add(sx, xs[sw]);
-                    sa = f2add(sa, xs[N + sw]);
+                    if (AUTOS) sa = f2add(sa, xs[N + sw]);
                 }
                 px[o] = sx;
-                pa[o] = sa;
+                if (AUTOS) pa[o] = sa;
             }
             __syncthreads();       // the next segment's first exchange stores must not overtake these reads
         }

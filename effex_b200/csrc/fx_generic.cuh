@@ -406,11 +406,15 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__rest
     const int s0 = blk_first ? blk_first[b] : b;
     const int s1 = blk_first ? blk_first[b + 1] : b + 1;
     float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
+    const bool autos = auto0 || auto1;            // part_a is not written when nobody asked for auto-powers
     for (int s = s0; s < s1; ++s) {
         const long long o = (long long)s * N + c;
         const float2 x = part_x[o];
-        const float2 a = part_a[o];
-        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+        xr += x.x; xi += x.y;
+        if (autos) {
+            const float2 a = part_a[o];
+            a0 += a.x; a1 += a.y;
+        }
     }
     xr *= inv_frames; xi *= inv_frames;
     const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);

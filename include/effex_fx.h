@@ -37,14 +37,15 @@
 extern "C" {
 #endif
 
-#define FX_ABI_VERSION 1
+#define FX_ABI_VERSION 2
 
 typedef enum {
     FX_OK = 0,
     FX_ERR_INVALID = -1,      /* bad argument (Python wrapper raises ValueError)      */
     FX_ERR_CUDA = -2,         /* CUDA runtime failure                                  */
     FX_ERR_UNSUPPORTED = -3,  /* shape outside the supported set (e.g. ntaps > 32)     */
-    FX_ERR_STATE = -4         /* call order (e.g. fx_process before fx_set_taps)       */
+    FX_ERR_STATE = -4,        /* call order (e.g. fx_process before fx_set_taps)       */
+    FX_ERR_COMM = -5          /* cross-GPU reduce: no peer access, or a rank never arrived */
 } fx_status;
 
 typedef struct fx_handle fx_handle;
@@ -124,6 +125,41 @@ int fx_span_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64
 int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
                         const uint8_t *d_halo0, const uint8_t *d_halo1, const uint64_t *h_sums, int64_t total_samp,
                         double *d_acc_x, double *d_acc_a0, double *d_acc_a1, double *d_frames);
+
+/* ---- multi-GPU: the one collective of the path (SURVEY 8(b) `fx_reduce`, 8(e)) ---------------------------
+ * The reference is single-GPU; north_star shards a recording by contiguous time blocks over the GPUs of a
+ * box and combines the small per-integration accumulators (effex.py:520-521's frame mean, taken over all
+ * ranks' frames) with ONE reduce.  The library owns that reduce: every handle has a MAILBOX in its HBM that
+ * its peers map over NVLink (cudaIpc), a rank's contribution is written straight into the root's mailbox by
+ * the kernel that folds the call's partial sums, and the root adds the world contributions in rank order
+ * (deterministic float64) on a side stream -- no library collective, no extra launch on non-root ranks.
+ *
+ *   fx_comm_export   every rank: create this handle's mailbox for `world` ranks with slots of at least
+ *                    slot_bytes (0 = the accumulators only; the lag search needs 8*M bytes, M = 2^ceil(log2 2n))
+ *                    and write its FX_COMM_TOKEN_BYTES token to h_token.  Synchronous.
+ *   (the host exchanges tokens with whatever it has: torch.distributed, MPI, a file)
+ *   fx_comm_attach   every rank: h_tokens = the world tokens in rank order.  Maps the peers' mailboxes.
+ *   fx_process_reduce / fx_integrate_stream_reduce
+ *                    fx_process_acc / fx_integrate_stream whose sums are ADDED to the root's accumulators
+ *                    d_acc_flat = double[4N+1] = [acc_x (2N) | acc_a0 (N) | acc_a1 (N) | frames (1)]
+ *                    (ignored on the other ranks).  COLLECTIVE: every rank of the world makes the same
+ *                    sequence of reduce calls with the same root.  Asynchronous; the root's accumulators are
+ *                    complete after fx_sync(), or for later work on fx_stream() after fx_comm_fence().
+ *   fx_reduce_f64/f32  in-place sum of d_buf[n] over the ranks into the root's d_buf (collective; the lag
+ *                    search reduces its accumulated 2n-point cross-spectrum with it); fenced on fx_stream().
+ * A rank that waits ~10 s for a peer gives up and the next fx_sync() returns FX_ERR_COMM. All ranks must
+ * fx_sync() (and the host must barrier) before any of them destroys its handle.                           */
+#define FX_COMM_TOKEN_BYTES 128
+int fx_comm_export(fx_handle *h, int world, size_t slot_bytes, void *h_token);
+int fx_comm_attach(fx_handle *h, int rank, int world, const void *h_tokens);
+int fx_comm_fence(fx_handle *h);
+int fx_process_reduce(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                      float *d_xspec, float *d_auto0, float *d_auto1, int root, double *d_acc_flat);
+int fx_integrate_stream_reduce(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                               const uint8_t *d_halo0, const uint8_t *d_halo1, const uint64_t *h_sums,
+                               int64_t total_samp, int root, double *d_acc_flat);
+int fx_reduce_f64(fx_handle *h, double *d_buf, size_t n, int root);
+int fx_reduce_f32(fx_handle *h, float *d_buf, size_t n, int root);
 
 /* fx_process_host: fx_process with HOST buffers (pinned or pageable): H2D of
  * the raw bytes, compute, D2H of the rows, pipelined in chunks on two

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in _declared():
         assert hasattr(lib, name), name
-    assert lib.fx_abi_version() == 1
+    assert lib.fx_abi_version() == _lib.FX_ABI_VERSION == 2
 
 
 def test_config_struct_layout():
