@@ -54,10 +54,16 @@ SIGNATURES = {
     "fx_reduce_f64": (C.c_int, [_VP, _VP, C.c_size_t, C.c_int]),
     "fx_reduce_f32": (C.c_int, [_VP, _VP, C.c_size_t, C.c_int]),
     "fx_process_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "fx_copy_probe": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "fx_pfb_c64": (C.c_int, [_VP, _VP, _VP]),
     "fx_pfb_u8": (C.c_int, [_VP, _VP, _VP]),
     "fx_lag_c64": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "fx_lag_u8": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "fx_lag_fft_len": (C.c_int64, [_VP]),
+    "fx_lag_accumulate_u8": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, C.c_int]),
+    "fx_lag_accumulate_c64": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, C.c_int]),
+    "fx_lag_finish": (C.c_int, [_VP, _VP, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "fx_lag_finish_async": (C.c_int, [_VP, _VP, _VP, _VP]),
     "fx_csv_rows_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fx_csv_format_rows": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fx_dev_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),

@@ -857,12 +857,10 @@ int fft_global(fx_handle *h, float2 *buf, float2 *tmp, long long M, int rows, in
     return FX_OK;
 }
 
+// accumulate sum_b FFT_M(pad(a_b)) * conj(FFT_M(pad(b_b))) over the n_blocks block pairs into d_xacc[M]
+// (natural order; first != 0 overwrites)
 template <bool U8>
-int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, int64_t *imax, float nbhd[3]) {
-    if (!h) return FX_ERR_INVALID;
-    if (!d0 || !d1 || !imax || !nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
-    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
-    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+int lag_accumulate_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, float2 *d_xacc, int first) {
     const long long n = h->cfg.num_samp;
     long long M = 2;
     while (M < 2 * n) M <<= 1;
@@ -880,11 +878,23 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
         FX_LAUNCH_CHECK(h, "lag_load");
         rc = fft_global(h, h->d_lag_rows, h->d_lag_tmp, M, 2, 0);
         if (rc) return rc;
-        fx::generic::lag_accum_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(h->d_lag_rows, M, b == 0,
-                                                                                        h->d_lag_acc);
+        fx::generic::lag_accum_kernel<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(h->d_lag_rows, M,
+                                                                                        first && b == 0, d_xacc);
         FX_LAUNCH_CHECK(h, "lag_accum");
     }
     if (U8) { rc = release_sums(h); if (rc) return rc; }
+    return FX_OK;
+}
+
+// inverse transform of the accumulated cross-spectrum + argmax; results on the device (d_lag_idx, d_lag_nb)
+int lag_finish_device(fx_handle *h, const float2 *d_xacc) {
+    const long long n = h->cfg.num_samp;
+    long long M = 2;
+    while (M < 2 * n) M <<= 1;
+    int rc = ensure_lag(h, M);
+    if (rc) return rc;
+    if (d_xacc != h->d_lag_acc)
+        FX_CUDA(h, cudaMemcpyAsync(h->d_lag_acc, d_xacc, sizeof(float2) * M, cudaMemcpyDeviceToDevice, h->stream));
     rc = fft_global(h, h->d_lag_acc, h->d_lag_acc_tmp, M, 1, 1);
     if (rc) return rc;
     const int nparts = (int)std::min<long long>(1024, (2 * n + 255) / 256);
@@ -894,6 +904,10 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     fx::generic::lag_argmax_stage2<<<1, 256, 0, h->stream>>>(h->d_lag_acc, n, M, h->d_pval, h->d_pidx, nparts, scale,
                                                             h->d_lag_idx, h->d_lag_nb);
     FX_LAUNCH_CHECK(h, "lag_argmax_stage2");
+    return FX_OK;
+}
+
+int lag_fetch(fx_handle *h, int64_t *imax, float nbhd[3]) {
     long long idx = 0;
     float nb[3];
     FX_CUDA(h, cudaMemcpyAsync(&idx, h->d_lag_idx, sizeof(idx), cudaMemcpyDeviceToHost, h->stream));
@@ -902,6 +916,24 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     *imax = idx;
     nbhd[0] = nb[0]; nbhd[1] = nb[1]; nbhd[2] = nb[2];
     return FX_OK;
+}
+
+template <bool U8>
+int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, int64_t *imax, float nbhd[3]) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d0 || !d1 || !imax || !nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
+    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    const long long n = h->cfg.num_samp;
+    long long M = 2;
+    while (M < 2 * n) M <<= 1;
+    int rc = ensure_lag(h, M);
+    if (rc) return rc;
+    rc = lag_accumulate_impl<U8>(h, d0, d1, n_blocks, h->d_lag_acc, 1);
+    if (rc) return rc;
+    rc = lag_finish_device(h, h->d_lag_acc);
+    if (rc) return rc;
+    return lag_fetch(h, imax, nbhd);
 }
 
 struct CommToken {                 // what fx_comm_export hands out (FX_COMM_TOKEN_BYTES = 128)
@@ -1285,8 +1317,8 @@ int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1
     return process_device(h, d_iq0, d_iq1, 1, nullptr, nullptr, nullptr, sink, &o);
 }
 
-int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,
-                    float *h_auto0, float *h_auto1) {
+static int host_pipeline(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,
+                         float *h_auto0, float *h_auto1, bool compute) {
     if (!h) return FX_ERR_INVALID;
     if (!h->taps_set) return fail(h, FX_ERR_STATE, "fx_set_taps must be called first");
     if (!h_iq0 || !h_iq1 || !h_xspec) return fail(h, FX_ERR_INVALID, "null pointer");
@@ -1327,9 +1359,11 @@ int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, in
         FX_CUDA(h, cudaEventRecord(h->ev_in[s], h->stream_copy));
         FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
         FX_CUDA(h, cudaStreamWaitEvent(h->stream_aux, h->ev_in[s], 0));
-        int rc = process_device(h, h->d_in[s][0], h->d_in[s][1], nb, h->d_out_x[s], h_auto0 ? h->d_out_a0[s] : nullptr,
-                                h_auto1 ? h->d_out_a1[s] : nullptr);
-        if (rc) return rc;
+        if (compute) {
+            int rc = process_device(h, h->d_in[s][0], h->d_in[s][1], nb, h->d_out_x[s], h_auto0 ? h->d_out_a0[s] : nullptr,
+                                    h_auto1 ? h->d_out_a1[s] : nullptr);
+            if (rc) return rc;
+        }
         FX_CUDA(h, cudaMemcpyAsync(h_xspec + 2 * (size_t)N * b0, h->d_out_x[s], sizeof(float2) * (size_t)N * nb,
                                    cudaMemcpyDeviceToHost, h->stream));
         if (h_auto0)
@@ -1342,6 +1376,15 @@ int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, in
     }
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     return FX_OK;
+}
+
+int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec,
+                    float *h_auto0, float *h_auto1) {
+    return host_pipeline(h, h_iq0, h_iq1, n_blocks, h_xspec, h_auto0, h_auto1, true);
+}
+
+int fx_copy_probe(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec) {
+    return host_pipeline(h, h_iq0, h_iq1, n_blocks, h_xspec, nullptr, nullptr, false);
 }
 
 int fx_pfb_c64(fx_handle *h, const float *d_x, float *d_frames) {
@@ -1382,6 +1425,47 @@ int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blo
 int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, int64_t *imax,
               float nbhd[3]) {
     return lag_impl<true>(h, d_iq0, d_iq1, n_blocks, imax, nbhd);
+}
+
+int64_t fx_lag_fft_len(const fx_handle *h) {
+    if (!h) return 0;
+    long long M = 2;
+    while (M < 2 * h->cfg.num_samp) M <<= 1;
+    return M;
+}
+int fx_lag_accumulate_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, float *d_xacc,
+                         int first) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d_iq0 || !d_iq1 || !d_xacc) return fail(h, FX_ERR_INVALID, "null pointer");
+    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return lag_accumulate_impl<true>(h, d_iq0, d_iq1, n_blocks, reinterpret_cast<float2 *>(d_xacc), first);
+}
+int fx_lag_accumulate_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blocks, float *d_xacc,
+                          int first) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d_x0 || !d_x1 || !d_xacc) return fail(h, FX_ERR_INVALID, "null pointer");
+    if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return lag_accumulate_impl<false>(h, d_x0, d_x1, n_blocks, reinterpret_cast<float2 *>(d_xacc), first);
+}
+int fx_lag_finish(fx_handle *h, const float *d_xacc, int64_t *imax, float nbhd[3]) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d_xacc || !imax || !nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = lag_finish_device(h, reinterpret_cast<const float2 *>(d_xacc));
+    if (rc) return rc;
+    return lag_fetch(h, imax, nbhd);
+}
+int fx_lag_finish_async(fx_handle *h, const float *d_xacc, int64_t *d_imax, float *d_nbhd) {
+    if (!h) return FX_ERR_INVALID;
+    if (!d_xacc || !d_imax || !d_nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = lag_finish_device(h, reinterpret_cast<const float2 *>(d_xacc));
+    if (rc) return rc;
+    FX_CUDA(h, cudaMemcpyAsync(d_imax, h->d_lag_idx, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+    FX_CUDA(h, cudaMemcpyAsync(d_nbhd, h->d_lag_nb, 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    return FX_OK;
 }
 
 int fx_dev_alloc(fx_handle *h, size_t bytes, void **d_ptr) {

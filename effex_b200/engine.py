@@ -18,6 +18,10 @@ class FxError(RuntimeError):
     pass
 
 
+class FxCommError(FxError):
+    """cross-GPU reduce failed (no peer access, or a rank never arrived)"""
+
+
 def pfb_window(ntaps: int, nbins: int) -> np.ndarray:
     """Prototype filter of effex.py:126-127 (float64, host)."""
     L = int(ntaps) * int(nbins)
@@ -39,6 +43,8 @@ def _raise(lib, handle, rc, what):
     text = f"{what} failed ({rc}): {msg}"
     if rc in (_lib.FX_ERR_INVALID, _lib.FX_ERR_UNSUPPORTED):
         raise ValueError(text)
+    if rc == _lib.FX_ERR_COMM:
+        raise FxCommError(text)
     raise FxError(text)
 
 
@@ -151,6 +157,91 @@ class FxEngine:
         self._exit()
         return (x, a0, a1) if autos else x
 
+    # ---- the cross-GPU reduce, owned by the library (fx_comm_*) ---------------------------------
+    def comm_export(self, world: int, slot_bytes: int = 0) -> bytes:
+        """Create this engine's mailbox; returns the token the peers need (exchange it with any transport)."""
+        tok = C.create_string_buffer(_lib.FX_COMM_TOKEN_BYTES)
+        self._check(self.lib.fx_comm_export(self.h, int(world), int(slot_bytes), tok), "fx_comm_export")
+        return tok.raw
+
+    def comm_attach(self, rank: int, world: int, tokens) -> None:
+        blob = b"".join(tokens)
+        if len(blob) != world * _lib.FX_COMM_TOKEN_BYTES:
+            raise ValueError("need one token per rank")
+        self._check(self.lib.fx_comm_attach(self.h, int(rank), int(world), blob), "fx_comm_attach")
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    @property
+    def comm_attached(self) -> bool:
+        return getattr(self, "comm_world", 0) > 0
+
+    def comm_fence(self):
+        self._check(self.lib.fx_comm_fence(self.h), "fx_comm_fence")
+
+    def process_reduce(self, iq0, iq1, n_blocks: int | None = None, out=None, acc=None, root: int = 0,
+                       inputs_ready: bool = False):
+        """fx_process_reduce: rows of this rank's blocks + this call's sums ADDED into the root's
+        accumulators (acc["flat"] on the root; ignored elsewhere).  Collective over the attached world."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        if out is None:
+            x = torch.empty((n_blocks, self.nbins), dtype=torch.complex64, device=self.tdev)
+            a0 = a1 = None
+        else:
+            x, a0, a1 = out
+        self._enter(inputs_ready)
+        rc = self.lib.fx_process_reduce(self.h, p0, p1, n_blocks, x.data_ptr() if x is not None else None,
+                                        a0.data_ptr() if a0 is not None else None,
+                                        a1.data_ptr() if a1 is not None else None, int(root),
+                                        acc["flat"].data_ptr() if acc is not None else None)
+        self._check(rc, "fx_process_reduce")
+        self._exit()
+        return x
+
+    def integrate_stream_reduce(self, iq0, iq1, acc, n_blocks: int | None = None, halo0=None, halo1=None, sums=None,
+                                total_samp: int | None = None, root: int = 0):
+        """fx_integrate_stream_reduce: integrate_stream whose sums go to the root's accumulators."""
+        if n_blocks is None:
+            n_blocks = iq0.numel() // (2 * self.num_samp)
+        p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
+        ph0, ph1 = self._halo_ptrs(halo0, halo1)
+        csums = (C.c_uint64 * 4)(*[int(v) for v in sums]) if sums is not None else None
+        self._enter()
+        rc = self.lib.fx_integrate_stream_reduce(self.h, p0, p1, n_blocks, ph0, ph1, csums,
+                                                 int(total_samp) if total_samp else 0, int(root),
+                                                 acc["flat"].data_ptr() if acc is not None else None)
+        self._check(rc, "fx_integrate_stream_reduce")
+        self._exit()
+        return acc
+
+    def reduce_inplace(self, buf: torch.Tensor, root: int = 0):
+        """fx_reduce_f64 / fx_reduce_f32: buf (float64, float32 or complex64) summed over the ranks into
+        the root's buf.  Collective."""
+        if not buf.is_cuda or not buf.is_contiguous():
+            raise ValueError("reduce_inplace needs a contiguous CUDA tensor")
+        self._enter()
+        if buf.dtype == torch.float64:
+            rc = self.lib.fx_reduce_f64(self.h, buf.data_ptr(), buf.numel(), int(root))
+        elif buf.dtype == torch.float32:
+            rc = self.lib.fx_reduce_f32(self.h, buf.data_ptr(), buf.numel(), int(root))
+        elif buf.dtype == torch.complex64:
+            rc = self.lib.fx_reduce_f32(self.h, buf.data_ptr(), 2 * buf.numel(), int(root))
+        else:
+            raise ValueError("unsupported dtype")
+        self._check(rc, "fx_reduce")
+        self._exit()
+        return buf
+
+    def _halo_ptrs(self, halo0, halo1):
+        hb = 2 * (self.ntaps - 1) * self.nbins
+        if halo0 is None:
+            return None, None
+        for t in (halo0, halo1):
+            if t is None or t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.numel() != hb:
+                raise ValueError(f"halo must be a contiguous uint8 CUDA tensor of {hb} bytes")
+        return halo0.data_ptr(), halo1.data_ptr()
+
     def new_accumulators(self):
         """float64 accumulators of one integration: views into ONE flat buffer, so the cross-GPU
         reduce is a single collective on `acc["flat"]` and clearing is a single memset."""
@@ -188,13 +279,7 @@ class FxEngine:
         if n_blocks is None:
             n_blocks = iq0.numel() // (2 * self.num_samp)
         p0, p1 = self._raw(iq0, n_blocks), self._raw(iq1, n_blocks)
-        hb = 2 * (self.ntaps - 1) * self.nbins
-        ph0 = ph1 = None
-        if halo0 is not None:
-            for t in (halo0, halo1):
-                if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.numel() != hb:
-                    raise ValueError(f"halo must be a contiguous uint8 CUDA tensor of {hb} bytes")
-            ph0, ph1 = halo0.data_ptr(), halo1.data_ptr()
+        ph0, ph1 = self._halo_ptrs(halo0, halo1)
         csums = None
         if sums is not None:
             csums = (C.c_uint64 * 4)(*[int(v) for v in sums])
@@ -233,6 +318,11 @@ class FxEngine:
                                       a0.ctypes.data if autos else None, a1.ctypes.data if autos else None)
         self._check(rc, "fx_process_host")
         return (x, a0, a1) if autos else x
+
+    def copy_probe(self, raw0: np.ndarray, raw1: np.ndarray, n_blocks: int, out: np.ndarray):
+        """fx_copy_probe: the H2D/D2H traffic of process_host with no kernels (the roof of that path)."""
+        self._check(self.lib.fx_copy_probe(self.h, raw0.ctypes.data, raw1.ctypes.data, n_blocks, out.ctypes.data),
+                    "fx_copy_probe")
 
     # ---- pieces ---------------------------------------------------------------
     def pfb(self, x) -> torch.Tensor:
@@ -275,6 +365,37 @@ class FxEngine:
             self._enter()
             rc = self.lib.fx_lag_c64(self.h, ta.data_ptr(), tb.data_ptr(), n_blocks, C.byref(imax), nb)
         self._check(rc, "fx_lag")
+        return self.num_samp, int(imax.value), float(nb[0]), float(nb[1]), float(nb[2])
+
+    def lag_fft_len(self) -> int:
+        return int(self.lib.fx_lag_fft_len(self.h))
+
+    def lag_accumulate(self, a, b, n_blocks: int = 1, xacc: torch.Tensor | None = None, first: bool = True):
+        """fx_lag_accumulate_*: xacc[M] (complex64) (=|+=) sum over the block pairs of FFT(a)*conj(FFT(b))."""
+        if xacc is None:
+            xacc = torch.empty(self.lag_fft_len(), dtype=torch.complex64, device=self.tdev)
+            first = True
+        if isinstance(a, torch.Tensor) and a.dtype == torch.uint8:
+            p0, p1 = self._raw(a, n_blocks), self._raw(b, n_blocks)
+            self._enter()
+            rc = self.lib.fx_lag_accumulate_u8(self.h, p0, p1, n_blocks, xacc.data_ptr(), 1 if first else 0)
+        else:
+            ta, tb = self._as_c64(a), self._as_c64(b)
+            if ta.numel() != self.num_samp * n_blocks or tb.numel() != ta.numel():
+                raise ValueError("input length must equal n_blocks * num_samp")
+            self._enter()
+            rc = self.lib.fx_lag_accumulate_c64(self.h, ta.data_ptr(), tb.data_ptr(), n_blocks, xacc.data_ptr(),
+                                                1 if first else 0)
+        self._check(rc, "fx_lag_accumulate")
+        self._exit()
+        return xacc
+
+    def lag_finish(self, xacc: torch.Tensor):
+        """fx_lag_finish: (n, imax, xprev, xbest, xnext) from an accumulated cross-spectrum."""
+        imax = C.c_int64()
+        nb = (C.c_float * 3)()
+        self._enter()
+        self._check(self.lib.fx_lag_finish(self.h, xacc.data_ptr(), C.byref(imax), nb), "fx_lag_finish")
         return self.num_samp, int(imax.value), float(nb[0]), float(nb[1]), float(nb[2])
 
     # ---- measurement -----------------------------------------------------------

@@ -9,7 +9,11 @@ that span ranks (a whole-recording spectrum, the accumulated lag
 cross-spectrum): one reduce of the small float64 accumulators
 (N x {complex cross, auto0, auto1} + a frame count) to rank 0.
 
-`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the transport.
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing: rendezvous, the exchange
+of mailbox tokens, the 5-word all-reduce of byte sums and the halo all-gather of streaming mode.  The
+reduce of the accumulators itself is the library's own (fx_comm_*: peer-memory stores over NVLink fused
+into the integrate epilogue) once `attach_comm(engine)` has run; without it (CPU tests, or accumulators
+that do not come from an engine) `reduce_accumulators` uses `dist.reduce`.
 """
 from __future__ import annotations
 
@@ -31,10 +35,28 @@ def shard_range(n_blocks: int, world: int, rank: int):
     return start, count
 
 
-def reduce_accumulators(acc: dict, dst: int = 0, group=None) -> dict:
+def attach_comm(engine, group=None, slot_bytes: int = 0) -> bool:
+    """Create the engine's mailbox, exchange the tokens over `group` and map the peers (every rank calls
+    this).  Returns False -- and leaves the engine on the dist.reduce path -- when there is one rank only."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    tok = engine.comm_export(world, slot_bytes)
+    mine = torch.frombuffer(bytearray(tok), dtype=torch.uint8).to(engine.tdev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    engine.comm_attach(rank, world, [bytes(g.cpu().numpy().tobytes()) for g in gathered])
+    dist.barrier(group=group)          # every rank has mapped every mailbox before anyone pushes
+    return True
+
+
+def reduce_accumulators(acc: dict, dst: int = 0, group=None, engine=None) -> dict:
     """One reduce(sum) of the per-integration accumulators to `dst` (in place
     on dst; other ranks' tensors are left unspecified by the collective)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return acc
+    if engine is not None and engine.comm_attached and "flat" in acc:
+        engine.reduce_inplace(acc["flat"], root=dst)       # fx_reduce_f64: peer-memory push + rank-ordered fold
         return acc
     if "flat" in acc:                       # FxEngine.new_accumulators: already one buffer
         dist.reduce(acc["flat"], dst=dst, op=dist.ReduceOp.SUM, group=group)
@@ -86,7 +108,7 @@ def sharded_run(compute, n_blocks: int, group=None, dst: int = 0):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     start, count = shard_range(n_blocks, world, rank)
     rows, acc = compute(start, count)
-    acc = reduce_accumulators(acc, dst=dst, group=group)
+    acc = reduce_accumulators(acc, dst=dst, group=group, engine=getattr(compute, "engine", None))
     rows = gather_rows(rows, n_blocks, dst=dst, group=group)
     return rows, acc
 
@@ -101,6 +123,7 @@ def engine_compute(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor):
         lo, hi = 2 * S * start, 2 * S * (start + count)
         rows = engine.process(d_iq0[lo:hi], d_iq1[lo:hi], count, acc=acc)
         return rows, acc
+    compute.engine = engine
     return compute
 
 
@@ -109,24 +132,66 @@ def stream_integrate(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor, group=Non
     (rank r holds the r-th contiguous slice, a whole number of blocks, in d_iq0/d_iq1).
     Exchanges: (1) all-reduce of the 4 byte sums -> recording-wide DC mean; (2) the PFB halo, i.e. the
     last (ntaps-1)*nbins samples of the left neighbour's slice (all-gather of the tiny tails);
-    (3) one reduce of the float64 accumulators.  Returns the reduced accumulators (valid on dst)."""
+    (3) one reduce of the float64 accumulators (the library's own when attach_comm has run: the push is
+    fused into the integrate epilogue).  Returns the reduced accumulators (valid on dst).
+
+    Preconditions (checked): the tensors hold exactly a whole number of blocks; every rank's slice is a
+    whole number of FRAMES, so that the frame grid of the recording is the union of the ranks' grids
+    (a ragged slice would shift every later rank's frames and drop its own tail -- not the
+    one-giant-block semantics); a slice is at least as long as the halo."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    n_blocks = d_iq0.numel() // (2 * engine.num_samp)
+    S, N, T = engine.num_samp, engine.nbins, engine.ntaps
+    if d_iq0.numel() != d_iq1.numel() or d_iq0.numel() % (2 * S) != 0 or d_iq0.numel() == 0:
+        raise ValueError("each channel must hold the same whole number (>= 1) of blocks of 2*num_samp bytes")
+    n_blocks = d_iq0.numel() // (2 * S)
+    if n_blocks > getattr(engine, "max_blocks", n_blocks):
+        raise ValueError(f"slice of {n_blocks} blocks exceeds the engine's max_blocks = {engine.max_blocks}")
+    span = n_blocks * S
+    hb = 2 * (T - 1) * N
+    if world > 1 and span % N != 0:
+        raise ValueError(f"a rank's slice ({span} samples) must be a whole number of frames of {N} samples")
+    if world > 1 and 2 * span < hb:
+        raise ValueError("a rank's slice is shorter than the PFB halo")
     sums = torch.from_numpy(engine.span_sums(d_iq0, d_iq1, n_blocks).astype(np.int64)).to(d_iq0.device)
-    count = torch.tensor([n_blocks * engine.num_samp], dtype=torch.int64, device=d_iq0.device)
+    count = torch.tensor([span], dtype=torch.int64, device=d_iq0.device)
     halo0 = halo1 = None
     if world > 1:
         both = torch.cat([sums, count])
         dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
         sums, count = both[:4], both[4:]
-        hb = 2 * (engine.ntaps - 1) * engine.nbins
-        tails = torch.stack([d_iq0[-hb:], d_iq1[-hb:]]).contiguous()
+        end = 2 * span                       # the halo is the tail of the SPAN
+        tails = torch.stack([d_iq0[end - hb:end], d_iq1[end - hb:end]]).contiguous()
         gathered = [torch.empty_like(tails) for _ in range(world)]
         dist.all_gather(gathered, tails, group=group)
         if rank > 0:
             halo0, halo1 = gathered[rank - 1][0].contiguous(), gathered[rank - 1][1].contiguous()
     acc = engine.new_accumulators()
-    engine.integrate_stream(d_iq0, d_iq1, acc, n_blocks, halo0, halo1, sums.cpu().numpy().astype(np.uint64),
-                            int(count.item()))
+    h_sums, total = sums.cpu().numpy().astype(np.uint64), int(count.item())
+    if world > 1 and getattr(engine, "comm_attached", False):
+        engine.integrate_stream_reduce(d_iq0, d_iq1, acc, n_blocks, halo0, halo1, h_sums, total, root=dst)
+        engine.sync()
+        return acc
+    engine.integrate_stream(d_iq0, d_iq1, acc, n_blocks, halo0, halo1, h_sums, total)
     return reduce_accumulators(acc, dst=dst, group=group)
+
+
+def sharded_lag(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor, group=None, dst: int = 0):
+    """Delay calibration over a time-sharded recording (reference effex.py:583-627 on one
+    block): every rank accumulates FFT(a)*conj(FFT(b)) over ITS blocks, ONE reduce of the 2n-point
+    cross-spectrum (complex64[M], 4 MiB at n = 2^18) to `dst`, then the inverse transform and the argmax
+    on `dst`.  `engine` is a lag engine (num_samp = n; see Correlator._estimate_delay_gaussian).
+    Returns (n, imax, xprev, xbest, xnext) on dst, None elsewhere."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_blocks = d_iq0.numel() // (2 * engine.num_samp)
+    xacc = engine.lag_accumulate(d_iq0, d_iq1, n_blocks)
+    if world > 1:
+        if getattr(engine, "comm_attached", False):
+            engine.reduce_inplace(xacc, root=dst)
+        else:
+            flat = torch.view_as_real(xacc)
+            dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    if rank != dst:
+        return None
+    return engine.lag_finish(xacc)

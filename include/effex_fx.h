@@ -168,6 +168,11 @@ int fx_reduce_f32(fx_handle *h, float *d_buf, size_t n, int root);
 int fx_process_host(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks,
                     float *h_xspec, float *h_auto0, float *h_auto1);
 
+/* fx_copy_probe: the copies of fx_process_host and nothing else (same chunks, streams and staging buffers,
+ * no kernels; h_xspec receives stale staging contents).  bench.py times it beside fx_process_host: it is the
+ * PCIe/host-memory roof of the host-buffer path on the box at hand.                                         */
+int fx_copy_probe(fx_handle *h, const uint8_t *h_iq0, const uint8_t *h_iq1, int64_t n_blocks, float *h_xspec);
+
 /* ---- pieces exposed for the reference's own tests -----------------------
  * fx_pfb_c64: Correlator._spectrometer_poly(x, ntaps, n_branches, window)
  * (effex.py:530-555) on a complex64 device array of num_samp samples:
@@ -190,6 +195,21 @@ int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blo
                int64_t *imax, float nbhd[3]);
 int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
               int64_t *imax, float nbhd[3]);
+
+/* The same search in two halves, for accumulations that span calls or GPUs ("reduce the 2n-point
+ * accumulated cross-spectrum and IFFT on rank 0"):
+ *   fx_lag_fft_len         M = 2^ceil(log2(2*num_samp)), the length of the zero-padded transforms
+ *   fx_lag_accumulate_*    d_xacc[M] (complex64, natural order) (=|+=) sum_b FFT(a_b)*conj(FFT(b_b)); first != 0
+ *                          overwrites.  Asynchronous on fx_stream.
+ *   fx_lag_finish          inverse transform of d_xacc (left intact) + argmax as in fx_lag_*; synchronous.
+ *   fx_lag_finish_async    the same with the results left on the device (int64 d_imax[1], float d_nbhd[3]).    */
+int64_t fx_lag_fft_len(const fx_handle *h);
+int fx_lag_accumulate_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,
+                         float *d_xacc, int first);
+int fx_lag_accumulate_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blocks,
+                          float *d_xacc, int first);
+int fx_lag_finish(fx_handle *h, const float *d_xacc, int64_t *imax, float nbhd[3]);
+int fx_lag_finish_async(fx_handle *h, const float *d_xacc, int64_t *d_imax, float *d_nbhd);
 
 /* ---- CSV rows (host side; replaces np.savetxt in Correlator._write_data, effex.py:687-696) ----
  * Formats n_rows rows of nbins complex64 values exactly as `np.savetxt(fh, [row], delimiter=',')`

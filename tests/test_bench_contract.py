@@ -30,7 +30,7 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
-    assert "workload" in d["config"]
+    assert set(d["config"]) == {"workload", "parallelism", "l2"}
 
 
 def test_reference_arm_other_ranks_stay_silent():
@@ -51,7 +51,15 @@ def test_product_arm_line():
     assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 4 * 262144 * 550 and e["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert "fused_kernel_stag" in r["kernel"] and 0 < r["fp32_pipe"]["frac"] < 1
-    assert d["config"]["e2e_rows_match_device_rows"] is True
+    assert "fused_kernel_stag" in r["kernel"]
+    assert r["fp32_pipe"] is None or 0 < r["fp32_pipe"]["frac"] < 1
+    assert d["e2e_rows_match_device_rows"] is True
+    assert set(d["config"]) == {"workload", "parallelism", "l2"}          # identical in both arms
+    assert 0 < e["frac_of_copy_only"] <= 1.05 and e["copy_only"]["value"] > 0
+    c = d["configs"]
+    assert set(c) == {"c2", "c3", "c4", "c5"} and not any("error" in v for v in c.values()), c
+    assert c["c2"]["integer_lag"] == 37
+    assert c["c4"]["frames_integrated"] == c["c4"]["frames_expected"]
+    assert c["c5"]["csv_format"]["bytes"] > 0 and c["c3"]["value"] > 20_000
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
