@@ -108,10 +108,10 @@ struct fx_handle {
         char *local = nullptr;
         char *peer[fx::comm::kMaxWorld] = {};
         bool peer_ipc[fx::comm::kMaxWorld] = {};
-        unsigned int epoch = 0;
-        cudaStream_t stream_fold = nullptr;
-        cudaEvent_t ev_push = nullptr, ev_fold = nullptr;
-        bool fold_pending = false;
+        unsigned int epoch[fx::comm::kMaxWorld] = {};   // reduces so far PER ROOT (each root's mailbox has its own sequence)
+        // the root folds epoch e one collective call later (or in fx_comm_fence / fx_sync): by then the
+        // peers' pushes of epoch e have had a whole step to land, so the fold hardly ever spins
+        struct Pending { unsigned int epoch = 0; void *dst = nullptr; size_t n = 0; int accumulate = 0; bool f64 = true; } pending;
         long long timeout_cycles = 20000000000ll;    // ~10 s at 1.965 GHz
         double *d_acc_local = nullptr;               // [4N+1] staging for paths that run several stage-2 passes per call
     } comm;
@@ -399,7 +399,7 @@ int comm_begin(fx_handle *h, int root, fx::comm::PushTarget &t) {
     auto &c = h->comm;
     if (!c.attached) return fail(h, FX_ERR_STATE, "fx_comm_attach must be called first");
     if (root < 0 || root >= c.world) return fail(h, FX_ERR_INVALID, "reduce root out of range");
-    const unsigned int e = ++c.epoch;
+    const unsigned int e = ++c.epoch[root];
     const size_t par = e & 1u;
     char *base = comm_base(h, root);
     t.slot = base + c.off_slots + (par * c.world + c.rank) * c.slot_bytes;
@@ -410,38 +410,57 @@ int comm_begin(fx_handle *h, int root, fx::comm::PushTarget &t) {
     t.timeout_cycles = c.timeout_cycles;
     return FX_OK;
 }
-// root: fold the world slots of the current epoch into dst, on the fold stream, after this rank's own push
-template <typename T>
-int comm_end(fx_handle *h, int root, T *dst, size_t n, int accumulate) {
+// root: issue the fold of a pushed epoch on the handle's stream
+int comm_fold_now(fx_handle *h, const fx_handle::Comm::Pending &p) {
     auto &c = h->comm;
+    const size_t par = p.epoch & 1u;
+    const void *slots = c.local + c.off_slots + par * c.world * c.slot_bytes;
+    const unsigned int *flags = reinterpret_cast<const unsigned int *>(c.local + c.off_flags) + par * c.world * c.ctas;
+    unsigned int *done = reinterpret_cast<unsigned int *>(c.local + c.off_done);
+    unsigned int *err = reinterpret_cast<unsigned int *>(c.local);
+    if (p.f64)
+        fx::comm::fold_kernel<double><<<c.ctas, fx::comm::kThreads, 0, h->stream>>>(
+            reinterpret_cast<double *>(p.dst), p.n, slots, c.slot_bytes, flags, c.ctas, c.world, done, err, p.epoch,
+            p.accumulate, c.timeout_cycles);
+    else
+        fx::comm::fold_kernel<float><<<c.ctas, fx::comm::kThreads, 0, h->stream>>>(
+            reinterpret_cast<float *>(p.dst), p.n, slots, c.slot_bytes, flags, c.ctas, c.world, done, err, p.epoch,
+            p.accumulate, c.timeout_cycles);
+    FX_LAUNCH_CHECK(h, "comm_fold");
+    return FX_OK;
+}
+int comm_flush(fx_handle *h) {
+    auto &c = h->comm;
+    if (!c.pending.epoch) return FX_OK;
+    const auto p = c.pending;
+    c.pending = fx_handle::Comm::Pending();
+    return comm_fold_now(h, p);
+}
+// after this rank's push of the current epoch has been enqueued.  Root: fold the PREVIOUS pending epoch now
+// and leave this one pending (defer), or fold this one right away (in-place reduces whose result is used next).
+template <typename T>
+int comm_end(fx_handle *h, int root, T *dst, size_t n, int accumulate, bool defer) {
+    auto &c = h->comm;
+    int rc = comm_flush(h);
+    if (rc) return rc;
     if (root != c.rank) return FX_OK;
     if (!dst) return fail(h, FX_ERR_INVALID, "the reduce root needs a destination buffer");
-    FX_CUDA(h, cudaEventRecord(c.ev_push, h->stream));
-    FX_CUDA(h, cudaStreamWaitEvent(c.stream_fold, c.ev_push, 0));
-    const size_t par = c.epoch & 1u;
-    fx::comm::fold_kernel<T><<<c.ctas, fx::comm::kThreads, 0, c.stream_fold>>>(
-        dst, n, c.local + c.off_slots + par * c.world * c.slot_bytes, c.slot_bytes,
-        reinterpret_cast<const unsigned int *>(c.local + c.off_flags) + par * c.world * c.ctas, c.ctas, c.world,
-        reinterpret_cast<unsigned int *>(c.local + c.off_done), reinterpret_cast<unsigned int *>(c.local), c.epoch,
-        accumulate, c.timeout_cycles);
-    FX_LAUNCH_CHECK(h, "comm_fold");
-    FX_CUDA(h, cudaEventRecord(c.ev_fold, c.stream_fold));
-    c.fold_pending = true;
-    return FX_OK;
+    fx_handle::Comm::Pending p;
+    p.epoch = c.epoch[root]; p.dst = dst; p.n = n; p.accumulate = accumulate; p.f64 = sizeof(T) == 8;
+    if (defer) { c.pending = p; return FX_OK; }
+    return comm_fold_now(h, p);
 }
 template <typename T>
 int comm_reduce(fx_handle *h, T *d_buf, size_t n, int root) {
     auto &c = h->comm;
-    if (n * sizeof(T) > c.slot_bytes) return fail(h, FX_ERR_INVALID, "buffer larger than the mailbox slots of fx_comm_export");
+    if (c.attached && n * sizeof(T) > c.slot_bytes)
+        return fail(h, FX_ERR_INVALID, "buffer larger than the mailbox slots of fx_comm_export");
     fx::comm::PushTarget t;
     int rc = comm_begin(h, root, t);
     if (rc) return rc;
     fx::comm::push_kernel<T><<<c.ctas, fx::comm::kThreads, 0, h->stream>>>(d_buf, n, t);
     FX_LAUNCH_CHECK(h, "comm_push");
-    rc = comm_end<T>(h, root, d_buf, n, 0);
-    if (rc) return rc;
-    if (c.fold_pending) FX_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev_fold, 0));   // in place: order later users of d_buf
-    return FX_OK;
+    return comm_end<T>(h, root, d_buf, n, 0, false);
 }
 
 // stage 2 of an integration: fold the G group sums of scratch into the sink.  `staged` (paths that run
@@ -464,7 +483,7 @@ int launch_stage2(fx_handle *h, int NB, int G, double frames, const AccSink &sin
     if (rc) return rc;
     fx::comm::integrate_push_kernel<<<h->comm.ctas, fx::comm::kThreads, 0, h->stream>>>(h->d_int_scratch, NB, G, frames, t);
     FX_LAUNCH_CHECK(h, "integrate_push");
-    return comm_end<double>(h, sink.reduce_root, sink.flat, 4 * (size_t)NB + 1, 1);
+    return comm_end<double>(h, sink.reduce_root, sink.flat, 4 * (size_t)NB + 1, 1, true);
 }
 int sink_begin(fx_handle *h, int NB, const AccSink &sink, bool staged) {
     if (sink.reduce_root < 0) return FX_OK;
@@ -482,7 +501,7 @@ int sink_flush(fx_handle *h, int NB, const AccSink &sink, bool staged) {
     if (rc) return rc;
     fx::comm::push_kernel<double><<<h->comm.ctas, fx::comm::kThreads, 0, h->stream>>>(h->comm.d_acc_local, n, t);
     FX_LAUNCH_CHECK(h, "comm_push");
-    return comm_end<double>(h, sink.reduce_root, sink.flat, n, 1);
+    return comm_end<double>(h, sink.reduce_root, sink.flat, n, 1, true);
 }
 
 int launch_tail(fx_handle *h, const fx::bigfft::TailParams &prm, bool autos) {
@@ -956,12 +975,8 @@ void comm_release(fx_handle *h) {
     if (c.d_acc_local) cudaFree(c.d_acc_local);
     c.local = nullptr;
     c.d_acc_local = nullptr;
-    if (c.ev_push) cudaEventDestroy(c.ev_push);
-    if (c.ev_fold) cudaEventDestroy(c.ev_fold);
-    if (c.stream_fold) cudaStreamDestroy(c.stream_fold);
-    c.ev_push = c.ev_fold = nullptr;
-    c.stream_fold = nullptr;
-    c.exported = c.attached = c.fold_pending = false;
+    c.pending = fx_handle::Comm::Pending();
+    c.exported = c.attached = false;
 }
 
 // error word of the mailbox (set by a spin that hit its deadline); called with all streams idle
@@ -1168,7 +1183,6 @@ int fx_destroy(fx_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream_copy) cudaStreamSynchronize(h->stream_copy);
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
-    if (h->comm.stream_fold) cudaStreamSynchronize(h->comm.stream_fold);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
                     h->d_part_a, h->d_int_scratch, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
@@ -1202,11 +1216,11 @@ const char *fx_last_error(const fx_handle *h) { return h ? h->err.c_str() : g_cr
 int fx_sync(fx_handle *h) {
     if (!h) return FX_ERR_INVALID;
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc = comm_flush(h);                      // the root's deferred fold of the last reduce epoch
+    if (rc) return rc;
     FX_CUDA(h, cudaStreamSynchronize(h->stream_aux));
     FX_CUDA(h, cudaStreamSynchronize(h->stream));
     FX_CUDA(h, cudaStreamSynchronize(h->stream_copy));
-    if (h->comm.stream_fold) FX_CUDA(h, cudaStreamSynchronize(h->comm.stream_fold));
-    h->comm.fold_pending = false;
     return comm_check(h);
 }
 
@@ -1551,9 +1565,6 @@ int fx_comm_export(fx_handle *h, int world, size_t slot_bytes, void *h_token) {
     FX_CUDA(h, cudaMalloc(&c.local, c.local_bytes));
     FX_CUDA(h, cudaMemset(c.local, 0, c.local_bytes));
     FX_CUDA(h, cudaMalloc(&c.d_acc_local, acc_bytes));
-    FX_CUDA(h, cudaStreamCreateWithFlags(&c.stream_fold, cudaStreamNonBlocking));
-    FX_CUDA(h, cudaEventCreateWithFlags(&c.ev_push, cudaEventDisableTiming));
-    FX_CUDA(h, cudaEventCreateWithFlags(&c.ev_fold, cudaEventDisableTiming));
     FX_CUDA(h, cudaDeviceSynchronize());
     if (const char *e = getenv("EFFEX_FX_COMM_TIMEOUT_MS")) {
         const double ms = atof(e);
@@ -1573,7 +1584,7 @@ int fx_comm_export(fx_handle *h, int world, size_t slot_bytes, void *h_token) {
     memset(h_token, 0, FX_COMM_TOKEN_BYTES);
     memcpy(h_token, &tok, sizeof(tok));
     c.exported = true;
-    c.epoch = 0;
+    for (auto &e : c.epoch) e = 0;
     return FX_OK;
 }
 
@@ -1624,8 +1635,8 @@ int fx_comm_attach(fx_handle *h, int rank, int world, const void *h_tokens) {
 
 int fx_comm_fence(fx_handle *h) {
     if (!h) return FX_ERR_INVALID;
-    if (h->comm.fold_pending) FX_CUDA(h, cudaStreamWaitEvent(h->stream, h->comm.ev_fold, 0));
-    return FX_OK;
+    FX_CUDA(h, cudaSetDevice(h->cfg.device));
+    return comm_flush(h);
 }
 
 int fx_process_reduce(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks, float *d_xspec,

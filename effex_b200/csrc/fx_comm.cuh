@@ -9,13 +9,15 @@
 //   every rank (root too):  PUSH   its contribution straight into slot[parity][rank] of the ROOT's mailbox
 //                                   (plain 16-byte stores to the peer mapping, i.e. NVLink writes), then one
 //                                   st.release.sys of the epoch number per CTA into flag[parity][rank][cta];
-//   root only:              FOLD   CTA c spins (ld.acquire.sys) until flag[parity][r][c] == epoch for every r,
+//   root only:              FOLD   CTA c waits (ld.acquire.sys) until flag[parity][r][c] == epoch for every r,
 //                                   adds the world slots IN RANK ORDER (deterministic float64 sums) into the
 //                                   destination, and publishes done[c] = epoch.
 //
 // The push of an integration is fused into the kernel that folds the per-block partial sums
 // (integrate_push_kernel below = integrate_stage2_kernel + push), so a non-root rank adds NO launch to its
-// step; the root's fold runs on a side stream, off the critical path of the next step's fused kernel.
+// step.  The root issues the fold of epoch e one collective call LATER (at the end of step e+1, or in
+// fx_comm_fence / fx_sync): the peers' pushes have had a whole step to land, so the fold does not wait and
+// no rank's step ever stalls on another rank -- the ranks stay decoupled, as without a collective.
 // Back-pressure: a slot of parity p is rewritten at epoch e+2; the pusher first waits for done[c] >= e.
 // Epochs advance in lock step on all ranks (collective call order), as with any collective.
 // All spins carry a clock64() deadline and raise an error word instead of hanging the GPU.

@@ -132,7 +132,8 @@ int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1
  * ranks' frames) with ONE reduce.  The library owns that reduce: every handle has a MAILBOX in its HBM that
  * its peers map over NVLink (cudaIpc), a rank's contribution is written straight into the root's mailbox by
  * the kernel that folds the call's partial sums, and the root adds the world contributions in rank order
- * (deterministic float64) on a side stream -- no library collective, no extra launch on non-root ranks.
+ * (deterministic float64) one collective call later, when they have long landed -- no library collective, no
+ * extra launch on non-root ranks, no rank ever waiting for another inside a step.
  *
  *   fx_comm_export   every rank: create this handle's mailbox for `world` ranks with slots of at least
  *                    slot_bytes (0 = the accumulators only; the lag search needs 8*M bytes, M = 2^ceil(log2 2n))
@@ -143,10 +144,12 @@ int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1
  *                    fx_process_acc / fx_integrate_stream whose sums are ADDED to the root's accumulators
  *                    d_acc_flat = double[4N+1] = [acc_x (2N) | acc_a0 (N) | acc_a1 (N) | frames (1)]
  *                    (ignored on the other ranks).  COLLECTIVE: every rank of the world makes the same
- *                    sequence of reduce calls with the same root.  Asynchronous; the root's accumulators are
- *                    complete after fx_sync(), or for later work on fx_stream() after fx_comm_fence().
+ *                    sequence of reduce calls with the same root.  Asynchronous; the root folds an epoch at
+ *                    its NEXT collective call, so its accumulators are complete after fx_sync(), or for later
+ *                    work on fx_stream() after fx_comm_fence() (both issue the outstanding fold).
  *   fx_reduce_f64/f32  in-place sum of d_buf[n] over the ranks into the root's d_buf (collective; the lag
- *                    search reduces its accumulated 2n-point cross-spectrum with it); fenced on fx_stream().
+ *                    search reduces its accumulated 2n-point cross-spectrum with it); folded at once on
+ *                    fx_stream().  (One host thread driving several ranks must call the root last.)
  * A rank that waits ~10 s for a peer gives up and the next fx_sync() returns FX_ERR_COMM. All ranks must
  * fx_sync() (and the host must barrier) before any of them destroys its handle.                           */
 #define FX_COMM_TOKEN_BYTES 128

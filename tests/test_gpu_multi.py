@@ -87,7 +87,7 @@ def test_two_ranks_on_one_gpu_pipelined_epochs(N, S):
     acc1 = engs[1].new_accumulators()
     for r in (0, 1):
         engs[r].process_reduce(dv[r][0], dv[r][1], nb, acc=acc1 if r == 1 else None, root=1)
-    bufs = [torch.full((70001,), float(r + 1), dtype=torch.float32, device="cuda") for r in range(2)]
+    bufs = [torch.full((4 * N - 3,), float(r + 1), dtype=torch.float32, device="cuda") for r in range(2)]
     for r in (1, 0):
         engs[r].reduce_inplace(bufs[r], root=0)
     for eng in engs:

@@ -4,7 +4,7 @@ set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-  timeout ${TEST_TIMEOUT:-1500} python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > gpurun_out/pytest.log 2>&1; tail -25 gpurun_out/pytest.log
+  timeout ${TEST_TIMEOUT:-1500} python -m pytest ${PYTEST_ARGS:-tests} -m gpu -x -q > gpurun_out/pytest.log 2>&1; tail -25 gpurun_out/pytest.log
 fi
 if [ "${SKIP_BENCH:-0}" != "1" ]; then
   timeout 600 python bench.py --steps ${STEPS:-20} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json
