@@ -21,6 +21,7 @@ FX_ABI_VERSION = 2            # must equal FX_ABI_VERSION of include/effex_fx.h 
 FX_COMM_TOKEN_BYTES = 128
 FX_FLAG_FORCE_GENERIC = 1
 FX_FLAG_LOCKSTEP_KERNEL = 2
+FX_FLAG_CROSS_ONLY = 4
 
 
 class FxConfig(C.Structure):

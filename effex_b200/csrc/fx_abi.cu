@@ -84,6 +84,7 @@ struct fx_handle {
     bool parts_per_block = false;              // generic path: one partial per block
 
     double *d_int_scratch = nullptr;                              // integrate: [64][4N] partial sums
+    int *d_tile_counters = nullptr;                               // integrate tail: one ticket counter per 256-bin tile
     float2 *d_g0 = nullptr, *d_g1 = nullptr, *d_gtmp = nullptr;   // generic-path frame buffers
     size_t g_cap = 0;                                             // elements per buffer
 
@@ -383,6 +384,17 @@ int run_fused(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const Pa
 
 // capacity of the Z buffer in float4 elements (1 GiB); EFFEX_FX_Z_ELEMS shrinks it so that tests can walk
 // several chunks with small inputs
+// groups of blocks whose float64 sums are formed in parallel by finalize_integrate_kernel (<= 64: scratch;
+// EFFEX_FX_INT_GROUPS overrides for experiments)
+int int_groups() {
+    static int g = [] {
+        const char *e = getenv("EFFEX_FX_INT_GROUPS");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 64 ? v : 32;       // measured: 32 groups beat 64 (fewer, longer walks; a shorter tail)
+    }();
+    return g;
+}
+
 size_t z_budget() {
     if (const char *e = getenv("EFFEX_FX_Z_ELEMS")) {
         const long long v = atoll(e);
@@ -521,7 +533,7 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
     using namespace fx::bigfft;
     const int NB = h->cfg.nbins, G = 1 << h->logG, P = h->P;
     const long long S = h->cfg.num_samp;
-    const bool autos = d_auto0 || d_auto1 || sink.any();
+    const bool autos = d_auto0 || d_auto1 || (sink.any() && !(h->cfg.flags & FX_FLAG_CROSS_ONLY));
     int rc = launch_sums(h, d_iq0, d_iq1, n_blocks, S);
     if (rc) return rc;
     rc = sink_begin(h, NB, sink, true);
@@ -620,7 +632,7 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
         prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
         prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
         prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = n;
-        rc = launch_tail(h, prm, true);
+        rc = launch_tail(h, prm, !(h->cfg.flags & FX_FLAG_CROSS_ONLY));
         if (rc) return rc;
         integrate_kernel<<<dim3((NB + 255) / 256, 1), 256, 0, h->stream>>>(h->d_part_x, h->d_part_a, NB, h->logG,
                                                                            h->d_plan + h->off_blk, 1, h->d_int_scratch);
@@ -806,30 +818,77 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     if (h->big && !span && h->P <= 65535 && (size_t)h->P * h->cfg.nbins <= (size_t(1) << 27))
         return run_big(h, d_iq0, d_iq1, n_blocks, d_xspec, d_auto0, d_auto1, sink);
     PassOpts o = span ? *span : block_opts(h, n_blocks);
-    o.autos = d_auto0 || d_auto1 || sink.any();
+    o.autos = d_auto0 || d_auto1 || (sink.any() && !(h->cfg.flags & FX_FLAG_CROSS_ONLY));
     const int N = h->cfg.nbins;
     int rc = sink_begin(h, N, sink, false);
     if (rc) return rc;
     rc = run_parts(h, d_iq0, d_iq1, o);
     if (rc) return rc;
     if (sink.any()) {
+        // the fold of the per-group sums rides in the tail of the kernel that produces them (comm::integrate_tail)
+        const bool can_tail = N >= 256 && (N % 256) == 0;
+        fx::comm::IntegrateTail tail;
+        memset(&tail, 0, sizeof(tail));
+        int use_tail = 0;
+        auto &c = h->comm;
+        const bool root = sink.reduce_root >= 0 && sink.reduce_root == c.rank;
+        if (can_tail) {
+            use_tail = 1;
+            tail.autos = o.autos ? 1 : 0;
+            tail.counters = h->d_tile_counters;
+            if (sink.reduce_root < 0) {
+                tail.mode = 0;
+                tail.acc_x = sink.x; tail.acc_a0 = sink.a0; tail.acc_a1 = sink.a1; tail.acc_frames = sink.frames;
+            } else {
+                tail.mode = 1;
+                if (root && !sink.flat) return fail(h, FX_ERR_INVALID, "the reduce root needs a destination buffer");
+                // the root's pending fold of the previous epoch rides along when it has this shape
+                const bool take = root && c.pending.epoch && c.pending.f64 && c.pending.accumulate &&
+                                  c.pending.n == 4 * (size_t)N + 1;
+                if (!take) { rc = comm_flush(h); if (rc) return rc; }
+                rc = comm_begin(h, sink.reduce_root, tail.push);
+                if (rc) return rc;
+                if (take) {
+                    const size_t par = c.pending.epoch & 1u;
+                    tail.fold_epoch = c.pending.epoch;
+                    tail.fold_dst = reinterpret_cast<double *>(c.pending.dst);
+                    tail.fold_slots = c.local + c.off_slots + par * c.world * c.slot_bytes;
+                    tail.slot_stride_bytes = c.slot_bytes;
+                    tail.fold_flags = reinterpret_cast<const unsigned int *>(c.local + c.off_flags) + par * c.world * c.ctas;
+                    tail.flag_stride = c.ctas;
+                    tail.world = c.world;
+                    tail.done = reinterpret_cast<unsigned int *>(c.local + c.off_done);
+                    c.pending = fx_handle::Comm::Pending();
+                }
+            }
+        }
+        const double frames = (double)o.units * (double)o.P;
         int G;
         if (d_xspec) {
             // rows and accumulators from ONE pass over the partial sums
-            G = (int)std::max<long long>(1, std::min<long long>(64, n_blocks));
-            fx::generic::finalize_integrate_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
-                h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)n_blocks,
-                1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0,
-                d_auto1, h->d_int_scratch);
+            G = (int)std::max<long long>(1, std::min<long long>(int_groups(), n_blocks));
+#define FX_FIN_ARGS h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)n_blocks, \
+                1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0,         \
+                d_auto1, h->d_int_scratch, use_tail, frames, tail
+            if (o.autos)
+                fx::generic::finalize_integrate_kernel<true><<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(FX_FIN_ARGS);
+            else
+                fx::generic::finalize_integrate_kernel<false><<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(FX_FIN_ARGS);
+#undef FX_FIN_ARGS
             FX_LAUNCH_CHECK(h, "finalize_integrate");
         } else {
             const int n_segs = h->parts_per_block ? (int)o.units : (int)h->n_segs;
             G = std::max(1, std::min(64, n_segs / 4));
             fx::generic::integrate_stage1_kernel<<<dim3((N + 255) / 256, G), 256, 0, h->stream>>>(
-                h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch);
+                h->d_part_x, h->d_part_a, N, n_segs, h->d_int_scratch, o.autos ? 1 : 0, use_tail, frames, tail);
             FX_LAUNCH_CHECK(h, "integrate_stage1");
         }
-        return launch_stage2(h, N, G, (double)o.units * (double)o.P, sink, false);
+        if (!use_tail) return launch_stage2(h, N, G, frames, sink, false);
+        if (root) {      // this epoch is folded by the next collective call, fx_comm_fence or fx_sync
+            c.pending.epoch = c.epoch[c.rank]; c.pending.dst = sink.flat; c.pending.n = 4 * (size_t)N + 1;
+            c.pending.accumulate = 1; c.pending.f64 = true;
+        }
+        return FX_OK;
     }
     if (!d_xspec) return FX_OK;
     dim3 grid((N + 255) / 256, 1);
@@ -1083,6 +1142,10 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         CREATE_CUDA(cudaMalloc(&h->d_part_a, want * sizeof(float2)));
         h->part_cap = want;
         CREATE_CUDA(cudaMalloc(&h->d_int_scratch, sizeof(double) * 64 * 4 * (size_t)cfg->nbins));
+        CREATE_CUDA(cudaMemset(h->d_int_scratch, 0, sizeof(double) * 64 * 4 * (size_t)cfg->nbins));
+        const size_t tiles = std::max<size_t>(1, (size_t)cfg->nbins / 256);
+        CREATE_CUDA(cudaMalloc(&h->d_tile_counters, tiles * sizeof(int)));
+        CREATE_CUDA(cudaMemset(h->d_tile_counters, 0, tiles * sizeof(int)));
     }
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      3 * 4096 * (int)sizeof(float2)));
@@ -1185,7 +1248,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_int_scratch, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

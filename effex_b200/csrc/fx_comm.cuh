@@ -75,11 +75,8 @@ __device__ __forceinline__ void push_prologue(const PushTarget &t) {
     __syncthreads();
 }
 __device__ __forceinline__ void push_epilogue(const PushTarget &t) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys(t.flag + blockIdx.x, t.epoch);
-    }
+    __syncthreads();                                  // the CTA's stores happen-before thread 0's release
+    if (threadIdx.x == 0) st_release_sys(t.flag + blockIdx.x, t.epoch);
 }
 
 // generic contribution: n elements of T from src into the root's slot
@@ -135,9 +132,133 @@ __global__ void __launch_bounds__(kThreads) fold_kernel(T *__restrict__ dst, siz
         dst[i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        st_release_sys(done + blockIdx.x, epoch);
+    if (threadIdx.x == 0) st_release_sys(done + blockIdx.x, epoch);
+}
+
+// ---- the same push / fold as the TAIL of the kernel that produces the per-group partial sums -------------
+// finalize_integrate_kernel / integrate_stage1_kernel run a grid (N/256 bin tiles, G groups); the LAST CTA of
+// a bin tile to finish (ticket counter) folds the tile's G partials and, in one go,
+//   LOCAL  adds them to the caller's accumulators                       (fx_process_acc, fx_integrate)
+//   PUSH   writes them into the root's slot and releases the flags       (fx_process_reduce, any rank)
+//   +FOLD  on the root: also adds the world slots of the PREVIOUS epoch into the root's accumulators
+// so a step with accumulators and the cross-GPU reduce launches exactly the kernels of a step without.
+// A bin tile t (natural bins [256t, 256t+256)) covers these 256-element ranges of the flat accumulator
+// layout [x 2N | a0 N | a1 N | frames 1], i.e. these CTA indices of push_kernel/fold_kernel over 4N+1
+// elements (so the two forms interoperate on the same flags): 2t, 2t+1, N/128 + t, 3N/256 + t, and N/64
+// (the frame count) for tile 0.
+struct IntegrateTail {
+    int mode;                    // 0: local accumulators, 1: push
+    int autos;                   // a0/a1 parts carried
+    int *counters;               // [N/256] tickets, zero between calls
+    double *acc_x, *acc_a0, *acc_a1, *acc_frames;      // mode 0
+    PushTarget push;             // mode 1
+    // root only: fold of the pending epoch (fold_epoch != 0)
+    unsigned int fold_epoch;
+    double *fold_dst;            // flat [4N+1]
+    const void *fold_slots;      // slot[parity(fold_epoch)][0]
+    size_t slot_stride_bytes;
+    const unsigned int *fold_flags;   // flag[parity(fold_epoch)][0][0]
+    int flag_stride, world;
+    unsigned int *done;
+};
+
+__device__ __forceinline__ int tail_range_cta(int k, int tile, int N) {
+    return k == 0 ? 2 * tile : k == 1 ? 2 * tile + 1 : k == 2 ? N / 128 + tile : k == 3 ? 3 * N / 256 + tile : N / 64;
+}
+
+// called by every thread of a 256-thread CTA after it has written scratch[g][...] for bin tile `tile`
+// (natural order); c = this thread's natural bin (256*tile + something), G = gridDim.y
+__device__ __forceinline__ void integrate_tail(const IntegrateTail &t, const double *scratch, int N, int G, double frames,
+                                               int tile, int c, bool valid) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(t.counters + tile, 1) == G - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) t.counters[tile] = 0;
+    __threadfence();
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (valid) {
+        // G <= 64 group sums per value, added in group order; 8 independent loads in flight
+        for (int g0 = 0; g0 < G; g0 += 8) {
+            double2 x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                x[u] = __ldcg(reinterpret_cast<const double2 *>(scratch + (size_t)(g0 + u < G ? g0 + u : g0) * 4 * N + 2 * c));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (g0 + u < G) { v0 += x[u].x; v1 += x[u].y; }
+        }
+        if (t.autos) {
+            for (int g0 = 0; g0 < G; g0 += 8) {
+                double p[8], q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double *o = scratch + (size_t)(g0 + u < G ? g0 + u : g0) * 4 * N;
+                    p[u] = __ldcg(o + 2 * N + c);
+                    q[u] = __ldcg(o + 3 * N + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (g0 + u < G) { v2 += p[u]; v3 += q[u]; }
+            }
+        }
+    }
+    const int nr = tile == 0 ? 5 : 4;          // flag ranges of this tile
+    if (t.mode == 0) {
+        if (valid) {
+            t.acc_x[2 * c] += v0; t.acc_x[2 * c + 1] += v1;
+            if (t.autos) { t.acc_a0[c] += v2; t.acc_a1[c] += v3; }
+        }
+        if (tile == 0 && threadIdx.x == 0 && t.acc_frames) *t.acc_frames += frames;
+    } else {
+        if ((int)threadIdx.x < nr && t.push.epoch > 2) {
+            if (!spin_until(t.push.done + tail_range_cta(threadIdx.x, tile, N), t.push.epoch - 2, t.push.timeout_cycles))
+                atomicOr(t.push.err, kErrTimeoutPush);
+        }
+        __syncthreads();
+        double *slot = reinterpret_cast<double *>(t.push.slot);
+        if (valid) {
+            *reinterpret_cast<double2 *>(slot + 2 * c) = make_double2(v0, v1);
+            slot[2 * N + c] = t.autos ? v2 : 0.0;
+            slot[3 * N + c] = t.autos ? v3 : 0.0;
+        }
+        if (tile == 0 && threadIdx.x == 0) slot[4 * (size_t)N] = frames;
+        __syncthreads();
+        if ((int)threadIdx.x < nr) st_release_sys(t.push.flag + tail_range_cta(threadIdx.x, tile, N), t.push.epoch);
+    }
+    if (t.fold_epoch) {
+        // root: the world slots of the previous epoch, in rank order
+        if ((int)threadIdx.x < nr * t.world) {
+            const int r = threadIdx.x / nr, k = threadIdx.x % nr;
+            if (!spin_until(t.fold_flags + (size_t)r * t.flag_stride + tail_range_cta(k, tile, N), t.fold_epoch,
+                            t.push.timeout_cycles))
+                atomicOr(t.push.err, kErrTimeoutFold);
+        }
+        __syncthreads();
+        double *d = t.fold_dst;
+        if (valid) {
+            double2 ax = *reinterpret_cast<double2 *>(d + 2 * c);
+            double a0 = d[2 * N + c], a1 = d[3 * N + c];
+            for (int r = 0; r < t.world; ++r) {
+                const double *sl = reinterpret_cast<const double *>(reinterpret_cast<const char *>(t.fold_slots) + (size_t)r * t.slot_stride_bytes);
+                const double2 x = __ldcg(reinterpret_cast<const double2 *>(sl + 2 * c));
+                ax.x += x.x; ax.y += x.y;
+                a0 += __ldcg(sl + 2 * N + c);
+                a1 += __ldcg(sl + 3 * N + c);
+            }
+            *reinterpret_cast<double2 *>(d + 2 * c) = ax;
+            d[2 * N + c] = a0; d[3 * N + c] = a1;
+        }
+        if (tile == 0 && threadIdx.x == 0) {
+            double f = d[4 * (size_t)N];
+            for (int r = 0; r < t.world; ++r)
+                f += __ldcg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(t.fold_slots) + (size_t)r * t.slot_stride_bytes) + 4 * (size_t)N);
+            d[4 * (size_t)N] = f;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nr) st_release_sys(t.done + tail_range_cta(threadIdx.x, tile, N), t.fold_epoch);
     }
 }
 

@@ -5,9 +5,14 @@
 // the fused path on the device.
 #pragma once
 #include "fx_common.cuh"
+#include "fx_comm.cuh"
 
 #ifndef FX_SUMS_DP4A
 #define FX_SUMS_DP4A 0
+#endif
+
+#ifndef FX_FIN_CTAS
+#define FX_FIN_CTAS 5      // resident CTAs per SM of the finalize+integrate kernels (register cap; the tail may spill)
 #endif
 
 namespace fx {
@@ -426,65 +431,97 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__rest
 
 // finalize + integrate in one pass over the partial sums: thread (j, g) walks the blocks of group g,
 // writes each block's row like finalize_rows_kernel and adds the block's un-normalised sums (float64)
-// into scratch[g] in natural bin order -- integrate_stage2_kernel folds the G groups afterwards.
+// into scratch[g] in natural bin order.  The G groups are folded either by integrate_stage2_kernel
+// afterwards, or -- use_tail -- by the last CTA of each bin tile to finish (comm::integrate_tail), which
+// also delivers them: into the caller's accumulators, or into the reduce root's mailbox.
 // grid = (ceil(N/256), G)
-__global__ void __launch_bounds__(256) finalize_integrate_kernel(const float2 *__restrict__ part_x,
+template <bool AUTOS>
+__global__ void __launch_bounds__(256, FX_FIN_CTAS) finalize_integrate_kernel(const float2 *__restrict__ part_x,
                                                                  const float2 *__restrict__ part_a, int N,
                                                                  const int *__restrict__ blk_first, int n_blocks,
                                                                  float inv_frames, const float2 *__restrict__ rot,
                                                                  float2 *__restrict__ xspec, float *__restrict__ auto0,
-                                                                 float *__restrict__ auto1, double *__restrict__ scratch) {
+                                                                 float *__restrict__ auto1, double *__restrict__ scratch,
+                                                                 int use_tail, double frames,
+                                                                 const comm::IntegrateTail tail) {
+    constexpr bool autos = AUTOS;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
+    const bool valid = j < N;
     const int c = (j + (N >> 1)) & (N - 1);
     const int G = gridDim.y, g = blockIdx.y;
-    const int b0 = (int)((long long)n_blocks * g / G), b1 = (int)((long long)n_blocks * (g + 1) / G);
-    const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);
-    double dxr = 0, dxi = 0, da0 = 0, da1 = 0;
-    for (int b = b0; b < b1; ++b) {
-        const int s0 = blk_first ? blk_first[b] : b;
-        const int s1 = blk_first ? blk_first[b + 1] : b + 1;
+    if (valid) {
+        const int b0 = (int)((long long)n_blocks * g / G), b1 = (int)((long long)n_blocks * (g + 1) / G);
+        const float2 r = rot ? rot[c] : make_float2(1.f, 0.f);
+        double dxr = 0, dxi = 0, da0 = 0, da1 = 0;
+        // one flat walk over the group's segments, four loads in flight; a row is emitted at every block boundary
+        const int sA = blk_first ? blk_first[b0] : b0, sB = blk_first ? blk_first[b1] : b1;
+        int b = b0;
+        int next = b0 < b1 ? (blk_first ? blk_first[b0 + 1] : b0 + 1) : sB;
         float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
-        for (int s = s0; s < s1; ++s) {
-            const long long o = (long long)s * N + c;
-            const float2 x = part_x[o];
-            const float2 a = part_a[o];
-            xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+        for (int s4 = sA; s4 < sB; s4 += 4) {
+            float2 x[4], a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool in = s4 + u < sB;
+                const long long o = (long long)(in ? s4 + u : sA) * N + c;
+                x[u] = part_x[o];
+                a[u] = autos ? part_a[o] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sg = s4 + u;
+                if (sg >= sB) break;
+                xr += x[u].x; xi += x[u].y;
+                if (autos) { a0 += a[u].x; a1 += a[u].y; }
+                if (sg + 1 == next) {
+                    dxr += xr; dxi += xi;
+                    if (autos) { da0 += a0; da1 += a1; }
+                    xr *= inv_frames; xi *= inv_frames;
+                    xspec[(long long)b * N + j] = make_float2(xr * r.x + xi * r.y, xi * r.x - xr * r.y);
+                    if (autos && auto0) auto0[(long long)b * N + j] = a0 * inv_frames;
+                    if (autos && auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
+                    xr = xi = a0 = a1 = 0.f;
+                    ++b;
+                    next = b < b1 ? (blk_first ? blk_first[b + 1] : b + 1) : sB;
+                }
+            }
         }
-        dxr += xr; dxi += xi; da0 += a0; da1 += a1;
-        xr *= inv_frames; xi *= inv_frames;
-        xspec[(long long)b * N + j] = make_float2(xr * r.x + xi * r.y, xi * r.x - xr * r.y);
-        if (auto0) auto0[(long long)b * N + j] = a0 * inv_frames;
-        if (auto1) auto1[(long long)b * N + j] = a1 * inv_frames;
+        double *o = scratch + (long long)g * 4 * N;
+        *reinterpret_cast<double2 *>(o + 2 * c) = make_double2(dxr, dxi);
+        o[2 * N + c] = da0;
+        o[3 * N + c] = da1;
     }
-    double *o = scratch + (long long)g * 4 * N;
-    o[2 * c] = dxr;
-    o[2 * c + 1] = dxi;
-    o[2 * N + c] = da0;
-    o[3 * N + c] = da1;
+    if (use_tail) comm::integrate_tail(tail, scratch, N, G, frames, c >> 8, c, valid);
 }
 
 // integrate: float64 accumulators += sum over all segments of the call (natural order, no rot).
 // Two deterministic stages: grid (ceil(N/256), G) partial sums over segment slices into scratch[G][4N],
-// then one pass that folds the G slices into the accumulators.
-__global__ void __launch_bounds__(256) integrate_stage1_kernel(const float2 *__restrict__ part_x,
+// then the fold of the G slices (integrate_stage2_kernel, or the tail as above).
+__global__ void __launch_bounds__(256, FX_FIN_CTAS) integrate_stage1_kernel(const float2 *__restrict__ part_x,
                                                                const float2 *__restrict__ part_a, int N, int n_segs,
-                                                               double *__restrict__ scratch) {
+                                                               double *__restrict__ scratch, int autos, int use_tail,
+                                                               double frames, const comm::IntegrateTail tail) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+    const bool valid = c < N;
     const int G = gridDim.y, g = blockIdx.y;
-    const int s0 = (int)((long long)n_segs * g / G), s1 = (int)((long long)n_segs * (g + 1) / G);
-    double xr = 0, xi = 0, a0 = 0, a1 = 0;
-    for (int s = s0; s < s1; ++s) {
-        const float2 x = part_x[(long long)s * N + c];
-        const float2 a = part_a[(long long)s * N + c];
-        xr += x.x; xi += x.y; a0 += a.x; a1 += a.y;
+    if (valid) {
+        const int s0 = (int)((long long)n_segs * g / G), s1 = (int)((long long)n_segs * (g + 1) / G);
+        double xr = 0, xi = 0, a0 = 0, a1 = 0;
+        for (int s = s0; s < s1; ++s) {
+            const float2 x = part_x[(long long)s * N + c];
+            xr += x.x; xi += x.y;
+            if (autos) {
+                const float2 a = part_a[(long long)s * N + c];
+                a0 += a.x; a1 += a.y;
+            }
+        }
+        double *o = scratch + (long long)g * 4 * N;
+        o[2 * c] = xr;
+        o[2 * c + 1] = xi;
+        o[2 * N + c] = a0;
+        o[3 * N + c] = a1;
     }
-    double *o = scratch + (long long)g * 4 * N;
-    o[2 * c] = xr;
-    o[2 * c + 1] = xi;
-    o[2 * N + c] = a0;
-    o[3 * N + c] = a1;
+    if (use_tail) comm::integrate_tail(tail, scratch, N, G, frames, c >> 8, c, valid);
 }
 __global__ void __launch_bounds__(256) integrate_stage2_kernel(const double *__restrict__ scratch, int N, int G,
                                                                double frames, double *__restrict__ acc_x,

@@ -51,14 +51,15 @@ def _raise(lib, handle, rc, what):
 class FxEngine:
     def __init__(self, num_samp: int, nbins: int, ntaps: int = 4, device: int = 0, max_blocks: int = 1,
                  dc_remove: bool = True, force_generic: bool = False, window: np.ndarray | None = None,
-                 lockstep_kernel: bool = False):
+                 lockstep_kernel: bool = False, cross_only: bool = False):
         self.lib = _lib.load()
         self.num_samp, self.nbins, self.ntaps = int(num_samp), int(nbins), int(ntaps)
         self.device = int(device)
         self.max_blocks = int(max_blocks)
         cfg = _lib.FxConfig(self.device, self.ntaps, self.nbins, 1 if dc_remove else 0, self.num_samp,
                             self.max_blocks, (_lib.FX_FLAG_FORCE_GENERIC if force_generic else 0)
-                            | (_lib.FX_FLAG_LOCKSTEP_KERNEL if lockstep_kernel else 0))
+                            | (_lib.FX_FLAG_LOCKSTEP_KERNEL if lockstep_kernel else 0)
+                            | (_lib.FX_FLAG_CROSS_ONLY if cross_only else 0))
         h = C.c_void_p()
         rc = self.lib.fx_create(C.byref(cfg), C.byref(h))
         if rc != _lib.FX_OK:

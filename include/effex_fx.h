@@ -62,6 +62,9 @@ typedef struct {
 
 #define FX_FLAG_FORCE_GENERIC 1   /* never take the fused kernels (used to cross-check them) */
 #define FX_FLAG_LOCKSTEP_KERNEL 2 /* fused path: use the simpler lock-step kernel instead of the staggered one */
+#define FX_FLAG_CROSS_ONLY 4      /* accumulators (fx_integrate*, fx_process_acc, fx_process_reduce) carry the cross-spectrum
+                                     and the frame count only -- what the reference outputs (effex.py:520-521); the auto-power
+                                     parts d_acc_a0/a1 are left untouched and the kernels skip |F|^2 (4 % fewer FP32 ops)       */
 
 /* ---- lifetime --------------------------------------------------------- */
 int fx_abi_version(void);

@@ -56,7 +56,25 @@ def test_reduce_world_of_one_equals_integrate():
     eng.close()
 
 
-@pytest.mark.parametrize("N,S", [(4096, 2**15), (1024, 2**13), (8192, 2**16)])
+def test_cross_only_accumulators_skip_the_auto_powers():
+    """FX_FLAG_CROSS_ONLY: the cross-spectrum and frame-count parts are bit-identical to the full
+    accumulators, the auto-power parts stay untouched; rows are the same rows."""
+    S, N, nb = 2**15, 4096, 5
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=5, seed=3)
+    d0, d1 = dev(raw0), dev(raw1)
+    full, lean = FxEngine(S, N, 4, max_blocks=nb), FxEngine(S, N, 4, max_blocks=nb, cross_only=True)
+    a, b = full.new_accumulators(), lean.new_accumulators()
+    b["a0"].fill_(7.0)
+    ra, rb = full.process(d0, d1, nb, acc=a), lean.process(d0, d1, nb, acc=b)
+    full.integrate(d0, d1, a, nb); lean.integrate(d0, d1, b, nb)
+    full.sync(); lean.sync()
+    assert torch.equal(ra, rb)
+    assert torch.equal(a["x"], b["x"]) and a["frames"].item() == b["frames"].item() == 2 * nb * (S // N)
+    assert torch.all(b["a0"] == 7.0) and torch.all(b["a1"] == 0.0) and torch.all(a["a0"] > 0)
+    full.close(); lean.close()
+
+
+@pytest.mark.parametrize("N,S", [(4096, 2**15), (1024, 2**13), (8192, 2**16), (128, 2**12)])
 def test_two_ranks_on_one_gpu_pipelined_epochs(N, S):
     """Two handles = two ranks.  Six reduce epochs are issued back to back without a host sync (parity
     slots are reused from epoch 3 on: the push waits for the root's fold of epoch e-2), alternating which
