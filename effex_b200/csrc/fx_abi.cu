@@ -15,6 +15,7 @@
 #include "fx_generic.cuh"
 #include "fx_bigfft.cuh"
 #include "fx_comm.cuh"
+#include "fx_lag.cuh"
 #include <unistd.h>
 
 namespace {
@@ -67,6 +68,7 @@ struct fx_handle {
     // staging buffer, all sized in fx_create -- the hot calls never allocate, synchronise or copy blockingly
     struct PlanSlot {
         long long units = -1, P = -1;
+        int logF = 0, min_fpc = 4;
         int *d_plan = nullptr, *h_pin = nullptr;   // [segments x4 | cta_first | blk_first]
         size_t n_segs = 0, off_cta = 0, off_blk = 0;
         int grid = 0;
@@ -90,6 +92,12 @@ struct fx_handle {
 
     float2 *d_lag_rows = nullptr, *d_lag_tmp = nullptr, *d_lag_acc = nullptr, *d_lag_acc_tmp = nullptr;
     long long lagM = 0;
+    bool lag_fast = false;                     // M = G*4096, G in [2, 256]: head/tail kernels (fx_lag.cuh)
+    int lag_logG = 0;
+    float4 *d_lag_z = nullptr;                 // Z[blocks of a chunk][G][4096]
+    size_t lag_z_cap = 0;                      // float4 elements
+    float4 *d_lag_twAp = nullptr, *d_lag_twBp = nullptr;   // the tail kernel's tables for 4096-point transforms
+    float2 *d_lag_twH = nullptr;               // W_M^(n2*k1), [G][4096]
     float *d_pval = nullptr;
     long long *d_pidx = nullptr;
     long long *d_lag_idx = nullptr;
@@ -146,6 +154,8 @@ int fail(fx_handle *h, int code, const std::string &msg) {
             return fail((h), FX_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(e_)); \
         (h)->launches++;                                                                         \
     } while (0)
+
+void build_stage_tables(int logF, std::vector<float4> &twAp, std::vector<float4> &twBp);
 
 bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
@@ -227,18 +237,20 @@ int ensure_parts(fx_handle *h, size_t n_segs, size_t bins_per_seg = 0) {
 // the first segment of a run starts inside a block (and has to re-ingest T-1 frames of history).
 // Plans are cached per (n_blocks, P): a repeated shape costs a table lookup; a new shape is built into the
 // least recently used slot's pinned buffer and uploaded with an asynchronous copy on the handle's stream.
-int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
+// min_fpc: a CTA is given at least this many frames (amortises its prologue) before more CTAs are used
+int plan_segments(fx_handle *h, long long n_blocks, long long P = 0, int logF = -1, int min_fpc = 4) {
     if (P <= 0) P = h->P;
+    if (logF < 0) logF = h->logF;
     fx_handle::PlanSlot *slot = nullptr;
     for (auto &pl : h->plans)
-        if (pl.units == n_blocks && pl.P == P) slot = &pl;
+        if (pl.units == n_blocks && pl.P == P && pl.logF == logF && pl.min_fpc == min_fpc) slot = &pl;
     if (!slot) {
         slot = &h->plans[0];
         for (auto &pl : h->plans)
             if (pl.last_use < slot->last_use) slot = &pl;
-        const long long Psf = (P + (1ll << h->logF) - 1) >> h->logF;      // the kernel walks super-frames of 2^logF frames
+        const long long Psf = (P + (1ll << logF) - 1) >> logF;            // the kernel walks super-frames of 2^logF frames
         const long long F = n_blocks * Psf;
-        const long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / 4));
+        const long long grid = std::min<long long>(h->num_sms, std::max<long long>(1, F / min_fpc));
         const size_t max_segs = (size_t)n_blocks + (size_t)grid;
         const size_t n_int_max = max_segs * 4 + (size_t)grid + 1 + (size_t)n_blocks + 1;
         if (n_int_max > h->plan_cap)
@@ -275,6 +287,8 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0) {
         slot->grid = (int)grid;
         slot->units = n_blocks;
         slot->P = P;
+        slot->logF = logF;
+        slot->min_fpc = min_fpc;
         // stream-ordered: kernels already queued with this slot's old plan finish before the copy lands
         FX_CUDA(h, cudaMemcpyAsync(slot->d_plan, flat, n_int * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         FX_CUDA(h, cudaEventRecord(slot->uploaded, h->stream));
@@ -903,6 +917,21 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     return FX_OK;
 }
 
+// n2 columns per CTA of the lag head kernel (smem = 2 * G * tn2 * 16 B); EFFEX_FX_LAG_TN2 for experiments
+int lag_tn2() {
+    static int v = [] {
+        const char *e = getenv("EFFEX_FX_LAG_TN2");
+        const int t = e ? atoi(e) : 0;
+        return (t == 4 || t == 8 || t == 16 || t == 32) ? t : 16;
+    }();
+    return v;
+}
+
+bool lag_force_generic() {
+    static bool v = [] { const char *e = getenv("EFFEX_FX_LAG_GENERIC"); return e && atoi(e) != 0; }();
+    return v;
+}
+
 int ensure_lag(fx_handle *h, long long M) {
     if (M == h->lagM) return FX_OK;
     for (float2 **p : {&h->d_lag_rows, &h->d_lag_tmp, &h->d_lag_acc, &h->d_lag_acc_tmp}) {
@@ -910,10 +939,42 @@ int ensure_lag(fx_handle *h, long long M) {
         *p = nullptr;
     }
     h->lagM = 0;
-    FX_CUDA(h, cudaMalloc(&h->d_lag_rows, sizeof(float2) * 2 * M));
-    FX_CUDA(h, cudaMalloc(&h->d_lag_tmp, sizeof(float2) * 2 * M));
+    h->lag_fast = M >= 2 * fx::fused4096::N && M <= 256 * fx::fused4096::N && !lag_force_generic() &&
+                  !(h->cfg.flags & FX_FLAG_FORCE_GENERIC);
+    h->lag_logG = h->lag_fast ? ilog2(M / fx::fused4096::N) : 0;
     FX_CUDA(h, cudaMalloc(&h->d_lag_acc, sizeof(float2) * M));
-    FX_CUDA(h, cudaMalloc(&h->d_lag_acc_tmp, sizeof(float2) * M));
+    if (!h->lag_fast) {
+        FX_CUDA(h, cudaMalloc(&h->d_lag_rows, sizeof(float2) * 2 * M));
+        FX_CUDA(h, cudaMalloc(&h->d_lag_tmp, sizeof(float2) * 2 * M));
+        FX_CUDA(h, cudaMalloc(&h->d_lag_acc_tmp, sizeof(float2) * M));
+    } else {
+        const int G = 1 << h->lag_logG;
+        std::vector<float2> twH((size_t)G * fx::fused4096::N);
+        for (int k1 = 0; k1 < G; ++k1)
+            for (int n2 = 0; n2 < fx::fused4096::N; ++n2) {
+                const double a = -2.0 * M_PI * (double)(((long long)k1 * n2) % M) / (double)M;
+                twH[(size_t)k1 * fx::fused4096::N + n2] = make_float2((float)cos(a), (float)sin(a));
+            }
+        if (h->d_lag_twH) cudaFree(h->d_lag_twH);
+        h->d_lag_twH = nullptr;
+        FX_CUDA(h, cudaMalloc(&h->d_lag_twH, twH.size() * sizeof(float2)));
+        FX_CUDA(h, cudaMemcpy(h->d_lag_twH, twH.data(), twH.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    if (h->lag_fast && !h->d_lag_twAp) {
+        std::vector<float4> twAp, twBp;
+        build_stage_tables(0, twAp, twBp);
+        FX_CUDA(h, cudaMalloc(&h->d_lag_twAp, twAp.size() * sizeof(float4)));
+        FX_CUDA(h, cudaMalloc(&h->d_lag_twBp, twBp.size() * sizeof(float4)));
+        FX_CUDA(h, cudaMemcpy(h->d_lag_twAp, twAp.data(), twAp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        FX_CUDA(h, cudaMemcpy(h->d_lag_twBp, twBp.data(), twBp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        const int head_smem = 2 * 4096 * (int)sizeof(float4) + 256 * (int)sizeof(float2);
+        FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
+        FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
+        FX_CUDA(h, cudaFuncSetAttribute(fx::bigfft::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(fx::bigfft::SmemT)));
+        FX_CUDA(h, cudaFuncSetAttribute(fx::bigfft::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(fx::bigfft::SmemT)));
+    }
     if (!h->d_pval) {
         FX_CUDA(h, cudaMalloc(&h->d_pval, sizeof(float) * 1024));
         FX_CUDA(h, cudaMalloc(&h->d_pidx, sizeof(long long) * 1024));
@@ -922,6 +983,42 @@ int ensure_lag(fx_handle *h, long long M) {
     }
     h->lagM = M;
     return FX_OK;
+}
+
+int ensure_lag_z(fx_handle *h, size_t elems) {
+    if (elems <= h->lag_z_cap) return FX_OK;
+    if (h->d_lag_z) cudaFree(h->d_lag_z);
+    h->d_lag_z = nullptr;
+    h->lag_z_cap = 0;
+    FX_CUDA(h, cudaMalloc(&h->d_lag_z, elems * sizeof(float4)));
+    h->lag_z_cap = elems;
+    return FX_OK;
+}
+
+// head -> Z -> tail over `nb` "frames" (block pairs, or the one row of the inverse): partial sums per segment
+template <bool U8>
+int lag_head_tail(fx_handle *h, const void *d0, const void *d1, long long n_in, long long block0, long long nb,
+                  int conj_in, bool autos) {
+    const int logG = h->lag_logG, G = 1 << logG;
+    const int tn2 = std::min(lag_tn2(), fx::fused4096::N >> logG);
+    const size_t smem = 2 * (size_t)G * tn2 * sizeof(float4) + (size_t)G * sizeof(float2);
+    for (long long r0 = 0; r0 < nb; r0 += 65535) {
+        const long long nr = std::min<long long>(65535, nb - r0);
+        dim3 grid(fx::fused4096::N / tn2, (unsigned)nr);
+        fx::lag::lag_head_kernel<U8><<<grid, 256, smem, h->stream>>>(d0, d1, n_in, logG, tn2, block0 + r0, h->d_sums,
+                                                                    h->cfg.dc_remove, conj_in, h->d_lag_twH,
+                                                                    h->d_lag_z + (size_t)r0 * G * fx::fused4096::N);
+        FX_LAUNCH_CHECK(h, "lag_head");
+    }
+    h->planning_big = true;
+    int rc = plan_segments(h, G, nb, 0, 1);         // virtual blocks k1, the block pairs in the role of frames
+    h->planning_big = false;
+    if (rc) return rc;
+    fx::bigfft::TailParams prm;
+    prm.z = h->d_lag_z; prm.twAp = h->d_lag_twAp; prm.twBp = h->d_lag_twBp;
+    prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
+    prm.part_x = h->d_part_x; prm.part_a = h->d_part_a; prm.G = G; prm.P = (int)nb;
+    return launch_tail(h, prm, autos);
 }
 
 // in-place (result in buf) global-memory FFT of `rows` rows of length M
@@ -949,6 +1046,24 @@ int lag_accumulate_impl(fx_handle *h, const void *d0, const void *d1, long long 
         rc = launch_sums(h, (const uint8_t *)d0, (const uint8_t *)d1, n_blocks);
         if (rc) return rc;
     }
+    if (h->lag_fast) {
+        // all block pairs of a chunk (Z <= 1 GiB) in three launches: head, tail (accumulates over the blocks
+        // in registers), fold
+        const long long chunk = std::max<long long>(1, std::min<long long>(n_blocks, (long long)(z_budget() / (size_t)M)));
+        rc = ensure_lag_z(h, (size_t)chunk * M);
+        if (rc) return rc;
+        for (long long b0 = 0; b0 < n_blocks; b0 += chunk) {
+            const long long nb = std::min(chunk, n_blocks - b0);
+            rc = lag_head_tail<U8>(h, d0, d1, n, b0, nb, 0, false);
+            if (rc) return rc;
+            fx::lag::lag_fold_kernel<<<(unsigned)(M / 256), 256, 0, h->stream>>>(h->d_part_x, h->lag_logG,
+                                                                                h->d_plan + h->off_blk,
+                                                                                first && b0 == 0, d_xacc);
+            FX_LAUNCH_CHECK(h, "lag_fold");
+        }
+        if (U8) { rc = release_sums(h); if (rc) return rc; }
+        return FX_OK;
+    }
     for (long long b = 0; b < n_blocks; ++b) {
         dim3 grid((unsigned)((M + 255) / 256), 2);
         fx::generic::lag_load_kernel<U8><<<grid, 256, 0, h->stream>>>(d0, d1, n, M, b, h->d_sums, h->cfg.dc_remove,
@@ -971,6 +1086,23 @@ int lag_finish_device(fx_handle *h, const float2 *d_xacc) {
     while (M < 2 * n) M <<= 1;
     int rc = ensure_lag(h, M);
     if (rc) return rc;
+    if (h->lag_fast) {
+        // IFFT(x) = conj(FFT(conj x)) / M and only |xc| matters: one "frame" through head + tail; the tail's
+        // auto-power partial of channel 0 is |FFT(conj x)|^2, read in place by the argmax kernels
+        rc = ensure_lag_z(h, (size_t)M);
+        if (rc) return rc;
+        rc = lag_head_tail<false>(h, d_xacc, nullptr, M, 0, 1, 1, true);
+        if (rc) return rc;
+        const int nparts = (int)std::min<long long>(1024, (2 * n + 255) / 256);
+        fx::lag::lag_argmax_big_stage1<<<nparts, 256, 0, h->stream>>>(h->d_part_a, h->d_plan + h->off_blk, h->lag_logG, n, M,
+                                                                     h->d_pval, h->d_pidx);
+        FX_LAUNCH_CHECK(h, "lag_argmax_stage1");
+        fx::lag::lag_argmax_big_stage2<<<1, 256, 0, h->stream>>>(h->d_part_a, h->d_plan + h->off_blk, h->lag_logG, n, M,
+                                                                h->d_pval, h->d_pidx, nparts, (float)(1.0 / (double)M),
+                                                                h->d_lag_idx, h->d_lag_nb);
+        FX_LAUNCH_CHECK(h, "lag_argmax_stage2");
+        return FX_OK;
+    }
     if (d_xacc != h->d_lag_acc)
         FX_CUDA(h, cudaMemcpyAsync(h->d_lag_acc, d_xacc, sizeof(float2) * M, cudaMemcpyDeviceToDevice, h->stream));
     rc = fft_global(h, h->d_lag_acc, h->d_lag_acc_tmp, M, 1, 1);
@@ -1012,6 +1144,36 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     rc = lag_finish_device(h, h->d_lag_acc);
     if (rc) return rc;
     return lag_fetch(h, imax, nbhd);
+}
+
+// tables of the staggered / tail kernels in stage-A/B REGISTER order, two registers per float4 (one LDS.128):
+// row 2g+h holds the twiddles of registers j = 4g+2h and j+1.  Stage A: register j writes tile
+// row_of(j) = frame slot * RP + k1' and carries W_NL^(t*k1'), NL = 4096 >> logF; stage B: register j holds
+// k2 = perm16(j) and carries W256^(n3*k2).
+void build_stage_tables(int logF, std::vector<float4> &twAp, std::vector<float4> &twBp) {
+    twAp.assign(8 * 256, make_float4(0, 0, 0, 0));
+    twBp.assign(8 * 16, make_float4(0, 0, 0, 0));
+    const int RP = 16 >> logF, NL = fx::fused4096::N >> logF;
+    auto wA = [&](int j, int t) {
+        const int k1p = fx::fused4096::row_of(logF, j) % RP;
+        const double a = -2.0 * M_PI * (double)((k1p * t) % NL) / (double)NL;
+        return make_float2((float)cos(a), (float)sin(a));
+    };
+    auto wB = [&](int k2, int n3) {
+        const double a = -2.0 * M_PI * (double)((k2 * n3) % 256) / 256.0;
+        return make_float2((float)cos(a), (float)sin(a));
+    };
+    for (int r = 0; r < 8; ++r) {
+        const int j = 2 * r;       // = 4g + 2h for r = 2g + h
+        for (int t = 0; t < 256; ++t) {
+            const float2 a = wA(j, t), b = wA(j + 1, t);
+            twAp[r * 256 + t] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        for (int n3 = 0; n3 < 16; ++n3) {
+            const float2 a = wB(fx::perm16(j), n3), b = wB(fx::perm16(j + 1), n3);
+            twBp[r * 16 + n3] = make_float4(a.x, a.y, b.x, b.y);
+        }
+    }
 }
 
 struct CommToken {                 // what fx_comm_export hands out (FX_COMM_TOKEN_BYTES = 128)
@@ -1126,7 +1288,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     {   // everything the hot calls need is sized here from max_blocks (no allocation or sync in fx_process):
         // plan slots (device + pinned staging), partial sums, integrate scratch, halo staging, Z
         const int G = h->big ? (1 << h->logG) : 1;
-        const size_t max_units = std::max<size_t>(std::min<size_t>((size_t)cfg->max_blocks * G, 65535), (size_t)G);
+        // (the lag search plans up to 256 virtual blocks whatever max_blocks is)
+        const size_t max_units = std::max<size_t>(std::min<size_t>((size_t)cfg->max_blocks * G, 65535), (size_t)std::max(G, 256));
         const size_t max_segs = std::max<size_t>(max_units, (size_t)cfg->max_blocks) + (size_t)h->num_sms;
         h->plan_cap = max_segs * 4 + (size_t)h->num_sms + 1 + std::max<size_t>(max_units, (size_t)cfg->max_blocks) + 1;
         for (auto &pl : h->plans) {
@@ -1169,30 +1332,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
             }
         CREATE_CUDA(cudaMemcpy(h->d_twA, twA.data(), twA.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CREATE_CUDA(cudaMemcpy(h->d_twB, twB.data(), twB.size() * sizeof(float2), cudaMemcpyHostToDevice));
-        // staggered kernel: tables in stage-A/B REGISTER order, two registers per float4 (one LDS.128):
-        // row 2g+h holds the twiddles of registers j = 4g+2h and j+1.  Stage A: register j writes
-        // tile row_of(j) = frame slot * RP + k1' and carries W_NL^(t*k1'), NL = nbins; stage B:
-        // register j holds k2 = perm16(j) and carries W256^(n3*k2).
-        std::vector<float4> twAp(8 * 256), twBp(8 * 16);
-        {
-            const int RP = 16 >> h->logF, NL = fx::fused4096::N >> h->logF;
-            auto wA = [&](int j, int t) {
-                const int k1p = fx::fused4096::row_of(h->logF, j) % RP;
-                const double a = -2.0 * M_PI * (double)((k1p * t) % NL) / (double)NL;
-                return make_float2((float)cos(a), (float)sin(a));
-            };
-            for (int r = 0; r < 8; ++r) {
-                const int j = 2 * r;       // = 4g + 2h for r = 2g + h
-                for (int t = 0; t < 256; ++t) {
-                    const float2 a = wA(j, t), b = wA(j + 1, t);
-                    twAp[r * 256 + t] = make_float4(a.x, a.y, b.x, b.y);
-                }
-                for (int n3 = 0; n3 < 16; ++n3) {
-                    const float2 a = twB[fx::perm16(j) * 16 + n3], b = twB[fx::perm16(j + 1) * 16 + n3];
-                    twBp[r * 16 + n3] = make_float4(a.x, a.y, b.x, b.y);
-                }
-            }
-        }
+        std::vector<float4> twAp, twBp;
+        build_stage_tables(h->logF, twAp, twBp);
         CREATE_CUDA(cudaMalloc(&h->d_twAp, twAp.size() * sizeof(float4)));
         CREATE_CUDA(cudaMalloc(&h->d_twBp, twBp.size() * sizeof(float4)));
         CREATE_CUDA(cudaMemcpy(h->d_twAp, twAp.data(), twAp.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -1248,7 +1389,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};
