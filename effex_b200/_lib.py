@@ -67,6 +67,7 @@ SIGNATURES = {
     "fx_lag_finish_async": (C.c_int, [_VP, _VP, _VP, _VP]),
     "fx_csv_rows_bound": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fx_csv_format_rows": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fx_csv_format_double": (C.c_int, [C.c_double, C.c_int, C.c_char_p]),
     "fx_dev_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
     "fx_dev_free": (C.c_int, [_VP, _VP]),
     "fx_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(_VP)]),

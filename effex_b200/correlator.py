@@ -226,6 +226,14 @@ class Correlator:
         from .csvio import append_rows
         append_rows(self.output_file, rows)
 
+    def _start_writer(self):
+        """The reference formats and writes rows in a thread of its own (effex.py:457-460, :687-696) so that
+        the loop never waits for the disk.  Same here: batches of rows go through a queue to one writer
+        thread (row order = queue order); formatting runs in the library (fx_csv_format_rows, ctypes drops
+        the GIL), so batch k is formatted and written while batch k+1 is on the GPU."""
+        from .csvio import RowWriter
+        return RowWriter(self.output_file)
+
     # ---- run over a recording ------------------------------------------------------
     def run_recording(self, raw0, raw1, write_csv=True, calibrate=True):
         """Process a two-channel recording (uint8 interleaved IQ, numpy).  Mirrors one
@@ -258,15 +266,20 @@ class Correlator:
             return np.zeros((0, self.nbins), dtype=np.complex64)
         eng = self._main_engine(max_blocks=min(self.batch_blocks, nb))
         out = np.empty((nb, self.nbins), dtype=np.complex64)
-        for b0 in range(0, nb, self.batch_blocks):
-            n = min(self.batch_blocks, nb - b0)
-            lo = 2 * S * (first + b0)
-            eng.process_host(raw0[lo:lo + 2 * S * n], raw1[lo:lo + 2 * S * n], n, out=out[b0:b0 + n])
-            chunk = out[b0:b0 + n]
-            if self.mode == 'CONTINUUM':
-                chunk = (chunk.astype(np.complex128).mean(axis=1) / self.bandwidth).reshape(-1, 1)
-            if write_csv:
-                self._write_data(chunk)
+        writer = self._start_writer() if write_csv else None
+        try:
+            for b0 in range(0, nb, self.batch_blocks):
+                n = min(self.batch_blocks, nb - b0)
+                lo = 2 * S * (first + b0)
+                eng.process_host(raw0[lo:lo + 2 * S * n], raw1[lo:lo + 2 * S * n], n, out=out[b0:b0 + n])
+                chunk = out[b0:b0 + n]
+                if self.mode == 'CONTINUUM':
+                    chunk = (chunk.astype(np.complex128).mean(axis=1) / self.bandwidth).reshape(-1, 1)
+                if writer:
+                    writer.put(chunk)              # formatted + written while the next batch computes
+        finally:
+            if writer:
+                writer.close()
         if self.mode == 'CONTINUUM':
             return out.astype(np.complex128).mean(axis=1) / self.bandwidth
         return out
@@ -293,13 +306,18 @@ def run_files(cor: "Correlator", path0: str, path1: str, write_csv: bool = True,
     reader = RecordingReader(path0, path1, S, batch_blocks=cor.batch_blocks, skip_blocks=skip)
     eng = cor._main_engine(max_blocks=max(1, min(cor.batch_blocks, reader.n_blocks)))
     rows = []
-    for raw0, raw1, first, nb in reader:
-        out = eng.process_host(raw0, raw1, nb)
-        if cor.mode == 'CONTINUUM':
-            out = (out.astype(np.complex128).mean(axis=1) / cor.bandwidth).reshape(-1, 1)
-        if write_csv:
-            cor._write_data(out)
-        rows.append(out)
+    writer = cor._start_writer() if write_csv else None
+    try:
+        for raw0, raw1, first, nb in reader:
+            out = eng.process_host(raw0, raw1, nb)
+            if cor.mode == 'CONTINUUM':
+                out = (out.astype(np.complex128).mean(axis=1) / cor.bandwidth).reshape(-1, 1)
+            if writer:
+                writer.put(out)
+            rows.append(out)
+    finally:
+        if writer:
+            writer.close()
     if not rows:
         return np.zeros((0, cor.nbins), dtype=np.complex64)
     out = np.concatenate(rows, axis=0)

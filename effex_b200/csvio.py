@@ -66,6 +66,46 @@ def append_rows(path, rows):
         fh.write(format_rows(rows))
 
 
+class RowWriter:
+    """Appends batches of rows to `path` from a thread of its own, in the order they were put
+    (the reference's `_write_data` thread, effex.py:457-460, :687-696).  A failure in the thread is
+    re-raised by the next put() or by close()."""
+
+    def __init__(self, path, depth: int = 4):
+        import queue
+        import threading
+        self.path = path
+        self.q = queue.Queue(maxsize=depth)
+        self.error = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            with open(self.path, 'ab') as fh:
+                while True:
+                    rows = self.q.get()
+                    if rows is None:
+                        return
+                    if self.error is None:
+                        fh.write(format_rows(rows))
+        except Exception as e:          # keep draining so that put() never blocks forever
+            self.error = e
+            while self.q.get() is not None:
+                pass
+
+    def put(self, rows):
+        if self.error is not None:
+            raise self.error
+        self.q.put(np.array(rows, copy=True))       # the caller may reuse its buffer
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
 def read_metadata(path) -> dict:
     with open(path) as fh:
         first = fh.readline().strip()

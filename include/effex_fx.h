@@ -225,6 +225,10 @@ int fx_lag_finish_async(fx_handle *h, const float *d_xacc, int64_t *d_imax, floa
 size_t fx_csv_rows_bound(int64_t n_rows, int64_t nbins);
 int fx_csv_format_rows(const float *h_rows, int64_t n_rows, int64_t nbins, int n_threads,
                        char *h_out, size_t out_cap, size_t *out_len);
+/* "%.18e" (plus_sign == 0) or "%+.18e" of one double exactly as printf writes it, from the formatter
+ * fx_csv_format_rows uses (exact integer arithmetic, no snprintf); returns the character count, no NUL
+ * (h_out must hold 32 bytes).                                                                         */
+int fx_csv_format_double(double v, int plus_sign, char *h_out);
 
 /* ---- memory helpers (so a non-torch host can drive the library) --------- */
 int fx_dev_alloc(fx_handle *h, size_t bytes, void **d_ptr);
