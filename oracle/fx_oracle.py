@@ -22,7 +22,10 @@ The oracle is pinned two ways (see `tests/golden/make_golden.py` and
      (cuSignal `channelize_poly`, version unpinned -- `requirements.txt` is
      empty) is restated from its published algorithm and pinned by the
      reference's own property tests (`tests/test_effex.py:62-121`; 32 + 14 + 14
-     parametrisations), which discriminate the sign/ordering conventions.
+     parametrisations), which discriminate the sign/ordering conventions, and
+     by `tests/golden/cusignal_standin.py`, a thread-by-thread loop form of
+     cuSignal's kernel that shares no code with this module; that stand-in --
+     not this module -- is what the fixtures of (1) were generated with.
 
 Each function cites the reference `file:line` it follows (paths relative to
 the reference checkout).

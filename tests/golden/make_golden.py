@@ -15,10 +15,10 @@ its methods (`_spectrometer_poly`, `_pfb_xcorr`, `_estimate_delay_gaussian`,
   cupy      -> numpy (array/zeros/fft/exp/conj/pi/argmax/abs/asnumpy/...)
   cusignal  -> scipy.signal.get_window / firwin (cuSignal's are ports of
                these); get_shared_mem -> np.zeros; filtering.channelize_poly
-               -> oracle.fx_oracle.channelize_poly (the published cuSignal
-               algorithm; it is third-party to the reference, so the fixture
-               pins everything in effex.py AROUND it, and the property tests
-               of tests/test_effex.py pin its conventions)
+               -> tests/golden/cusignal_standin.py, a thread-by-thread loop
+               form of cuSignal's channelizer kernel that shares NO code with
+               the oracle (so the spec0 / xspec fixtures pin the oracle's
+               channelizer -- tap order, zero fill, conjugations -- from outside)
   rtlsdr    -> a dummy RtlSdr that accepts attribute writes (no USB)
   matplotlib-> empty module (only imported, never used here)
 
@@ -55,7 +55,9 @@ def install_shims():
     cs.firwin = scipy.signal.firwin
     cs.get_shared_mem = lambda n, dtype=np.complex128: np.zeros(n, dtype=dtype)
     filt = types.ModuleType("cusignal.filtering")
-    filt.channelize_poly = orc.channelize_poly
+    sys.path.insert(0, HERE)
+    import cusignal_standin
+    filt.channelize_poly = cusignal_standin.channelize_poly      # NOT the oracle's
     cs.filtering = filt
     sys.modules["cusignal"] = cs
     sys.modules["cusignal.filtering"] = filt

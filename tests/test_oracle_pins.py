@@ -3,7 +3,10 @@
 (1) the reference's own DSP property tests, re-expressed against the oracle
     (reference tests/test_effex.py:62-121: 32 + 14 + 14 parametrisations);
 (2) fixtures produced by executing the reference's unmodified effex.py behind
-    numpy stand-ins (tests/golden/make_golden.py).
+    numpy stand-ins (tests/golden/make_golden.py);
+(3) the one third-party routine on the path, cuSignal's channelize_poly, against a thread-by-thread loop
+    form of cuSignal's kernel that shares no code with the oracle (tests/golden/cusignal_standin.py) --
+    the same stand-in make_golden.py installs, so (2) is not circular either.
 """
 import os
 
@@ -122,3 +125,25 @@ def test_pfb_fir_form_matches_channelizer():
     w = orc.pfb_fir(x, h, N)
     c = np.arange(N)
     np.testing.assert_allclose(np.exp(-2j * np.pi * c / N) * np.fft.fft(w, axis=1), F, atol=1e-12)
+
+
+# ---- (3) the oracle's channelizer vs an independent restatement of cuSignal's kernel --------------------------
+@pytest.mark.parametrize("N,T,S", [(64, 4, 1000), (256, 4, 4096), (32, 32, 32 * 40 + 5), (16, 9, 16 * 30),
+                                   (1024, 4, 8192), (8, 1, 64), (128, 16, 128 * 3), (64, 4, 64 * 2)])
+def test_channelize_poly_equals_the_kernel_shaped_stand_in(N, T, S):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import cusignal_standin
+    rng = np.random.default_rng(N + T)
+    x = rng.normal(size=S) + 1j * rng.normal(size=S)
+    h = orc.pfb_window(T, N) * (1 + 0.1 * rng.normal(size=T * N))      # no symmetry to hide an index reversal behind
+    a, b = cusignal_standin.channelize_poly(x, h, N), orc.channelize_poly(x, h, N)
+    assert a.shape == b.shape == (N, S // N)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-13 * np.abs(b).max())
+    with pytest.raises(NotImplementedError):
+        cusignal_standin.channelize_poly(x, np.ones(33 * 8), 8)
+
+
+def test_golden_fixtures_do_not_come_from_the_oracle_channelizer():
+    src = open(os.path.join(os.path.dirname(__file__), "golden", "make_golden.py")).read()
+    assert "cusignal_standin.channelize_poly" in src and "= orc.channelize_poly" not in src
