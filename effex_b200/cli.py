@@ -36,8 +36,9 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument('--loglevel', '-L', default='INFO', type=str,
                         choices=['INFO', 'WARNING', 'DEBUG', 'ERROR', 'CRITICAL'], dest='loglevel')
     # --- not in the reference -------------------------------------------------
-    parser.add_argument('--input0', default=None, help='raw uint8 interleaved IQ file, channel 0')
-    parser.add_argument('--input1', default=None, help='raw uint8 interleaved IQ file, channel 1')
+    parser.add_argument('--input0', default=None,
+                        help='raw uint8 interleaved IQ, channel 0: a file, or a FIFO fed by e.g. `rtl_sdr -d 0 -`')
+    parser.add_argument('--input1', default=None, help='raw uint8 interleaved IQ, channel 1 (file or FIFO)')
     parser.add_argument('--synthetic-delay', default=37, type=int,
                         help='without input files: synthetic correlated noise, channel 1 lagging by this many samples')
     parser.add_argument('--extended', action='store_true',
@@ -58,7 +59,8 @@ def main(argv=None):
     n_blocks = int(np.ceil(cor.run_time * cor.bandwidth / S))
     if args.input0 and args.input1 and args.mode != 'test':
         from .correlator import run_files
-        run_files(cor, args.input0, args.input1)          # streamed from disk in chunks of whole blocks
+        # streamed in chunks of whole blocks; a FIFO / pipe ends at EOF or after --time worth of blocks
+        run_files(cor, args.input0, args.input1, max_blocks=n_blocks)
     else:
         if args.input0 and args.input1:
             raw0 = np.fromfile(args.input0, dtype=np.uint8, count=2 * S * n_blocks)

@@ -285,17 +285,21 @@ class Correlator:
         return out
 
 
-def run_files(cor: "Correlator", path0: str, path1: str, write_csv: bool = True, calibrate: bool = True):
-    """Spectrum/continuum run over two raw recordings on disk, streamed chunk by chunk
-    (`ingest.RecordingReader`) through the host pipeline.  Same row semantics as run_recording."""
-    from .ingest import RecordingReader
+def run_files(cor: "Correlator", path0, path1, write_csv: bool = True, calibrate: bool = True,
+              max_blocks: int | None = None):
+    """Spectrum/continuum run over two raw byte sources streamed batch by batch through the host pipeline:
+    regular files (`ingest.RecordingReader`) or FIFOs / pipes / file objects fed by e.g. two `rtl_sdr`
+    processes (`ingest.StreamReader`; the reference's `_streaming` producers, effex.py:630-664).  Same row
+    semantics as run_recording: the first block pair calibrates the delay and yields no row (:399-401)."""
+    from .ingest import open_reader, _is_regular_file
     S = int(cor.num_samp)
     if cor.mode == 'TEST':
         raise ValueError("TEST mode sweeps the delay per block; use run_recording")
     if write_csv:
         cor._write_metadata()
+    seekable = _is_regular_file(path0) and _is_regular_file(path1)
     skip = 0
-    if calibrate:
+    if calibrate and seekable:
         head0 = np.fromfile(path0, dtype=np.uint8, count=2 * S)
         head1 = np.fromfile(path1, dtype=np.uint8, count=2 * S)
         if head0.size == 2 * S and head1.size == 2 * S:
@@ -303,12 +307,24 @@ def run_files(cor: "Correlator", path0: str, path1: str, write_csv: bool = True,
             cor.gpu_iq_1 = torch.from_numpy(head1).to(f"cuda:{cor.device}")
             cor._calibrate_task()
             skip = 1
-    reader = RecordingReader(path0, path1, S, batch_blocks=cor.batch_blocks, skip_blocks=skip)
-    eng = cor._main_engine(max_blocks=max(1, min(cor.batch_blocks, reader.n_blocks)))
+    reader = open_reader(path0, path1, S, batch_blocks=cor.batch_blocks, skip_blocks=skip,
+                         max_blocks=max_blocks if seekable or max_blocks is None else max_blocks)
+    eng = None
     rows = []
     writer = cor._start_writer() if write_csv else None
+    pending_cal = calibrate and not seekable          # a stream calibrates on the first block it delivers
     try:
         for raw0, raw1, first, nb in reader:
+            if pending_cal:
+                cor.gpu_iq_0 = torch.from_numpy(raw0[:2 * S]).to(f"cuda:{cor.device}")
+                cor.gpu_iq_1 = torch.from_numpy(raw1[:2 * S]).to(f"cuda:{cor.device}")
+                cor._calibrate_task()
+                pending_cal = False
+                raw0, raw1, nb = raw0[2 * S:], raw1[2 * S:], nb - 1
+                if nb == 0:
+                    continue
+            if eng is None:      # after the calibration: the rot table is built from the calibrated delay
+                eng = cor._main_engine(max_blocks=max(1, cor.batch_blocks))
             out = eng.process_host(raw0, raw1, nb)
             if cor.mode == 'CONTINUUM':
                 out = (out.astype(np.complex128).mean(axis=1) / cor.bandwidth).reshape(-1, 1)
