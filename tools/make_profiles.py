@@ -23,22 +23,41 @@ os.makedirs(os.path.join(P, "sass"), exist_ok=True)
 
 # ---- launch list ------------------------------------------------------------
 lc = os.path.join(G, "launches.csv")
+step_dram = None
 if os.path.exists(lc):
     lines = [l for l in open(lc) if not l.startswith("==")]
     rows = list(csv.reader(lines))
     hdr = rows[0]
-    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    d = defaultdict(list)
+    ki, vi, idi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("ID")
+    mi, ui = hdr.index("Metric Name"), hdr.index("Metric Unit")
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6}
+    launches = {}                     # id -> {name, time_ns, dram}
     for r in rows[1:]:
-        if len(r) > vi:
-            d[r[ki]].append(float(r[vi].replace(",", "")))
-    tot = sum(sum(v) for v in d.values())
+        if len(r) <= vi:
+            continue
+        L = launches.setdefault(r[idi], {"name": r[ki], "time": 0.0, "dram": 0.0})
+        v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1)
+        if r[mi].startswith("gpu__time_duration"):
+            L["time"] = v
+        elif r[mi].startswith("dram__bytes"):
+            L["dram"] += v
+    d = defaultdict(list)
+    for L in launches.values():
+        d[L["name"]].append(L)
+    tot = sum(L["time"] for L in launches.values())
+    # one step of bench.py --profile = byte sums + fused + finalize: traffic of a step = sum of the means
+    step_names = [k for k in d if any(t in k for t in ("block_sums_kernel", "fused_kernel_stag", "finalize_rows_kernel"))]
+    if step_names:
+        step_dram = sum(sum(L["dram"] for L in d[k]) / len(d[k]) for k in step_names)
     with open(os.path.join(P, f"{rnd}{tag}_launches.csv"), "w") as fh:
-        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --profile\n")
+        fh.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python bench.py --steps 2 --warmup 3 --profile\n")
         fh.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
-        fh.write("kernel,launches,mean_us,total_us,share\n")
-        for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
-            fh.write(f"\"{k}\",{len(v)},{sum(v) / len(v) / 1e3:.1f},{sum(v) / 1e3:.1f},{sum(v) / tot:.4f}\n")
+        if step_dram:
+            fh.write(f"# dram bytes of one step (byte sums + fused + finalize, means): {step_dram:.0f} = {step_dram / 594739200:.3f} x the algorithmic 594739200\n")
+        fh.write("kernel,launches,mean_us,total_us,share,mean_dram_MB\n")
+        for k, v in sorted(d.items(), key=lambda kv: -sum(L["time"] for L in kv[1])):
+            t = [L["time"] for L in v]
+            fh.write(f"\"{k}\",{len(v)},{sum(t) / len(t) / 1e3:.1f},{sum(t) / 1e3:.1f},{sum(t) / tot:.4f},{sum(L['dram'] for L in v) / len(v) / 1e6:.1f}\n")
         fh.write("# ---- raw list ----\n")
         fh.writelines(lines)
 
@@ -72,7 +91,7 @@ if os.path.exists(rep):
         return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
     with open(os.path.join(P, f"{rnd}{tag}_fused_ncu.txt"), "w") as fh:
         fh.write("# ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 3 -c 1 "
-                 "python bench.py --steps 1 --warmup 3 --profile\n# kernel: fx::fused4096::fused_kernel, "
+                 "python bench.py --steps 1 --warmup 3 --profile\n# kernel: fx::fused4096::fused_kernel_stag<0, false>, "
                  "550 block pairs (S=262144, N=4096, T=4)\n")
         for k in keys:
             if k in m:
@@ -82,10 +101,16 @@ if os.path.exists(rep):
                               input=src, capture_output=True, text=True).stdout
         fh.write("\n# ---- warp-stall sampling (SASS view) ----\n" + summ)
     traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-    json.dump({"dram_bytes_per_launch": traffic, "dram_bytes_read": num("dram__bytes_read.sum"),
-               "dram_bytes_write": num("dram__bytes_write.sum"), "source": f"profiles/{rnd}{tag}_fused_ncu.txt",
-               "kernel": "fx::fused4096::fused_kernel", "units_per_launch": "550 block pairs"},
-              open(os.path.join(P, "fused_traffic.json"), "w"), indent=1)
+    facts = {"dram_bytes_per_launch": traffic, "dram_bytes_read": num("dram__bytes_read.sum"),
+             "dram_bytes_write": num("dram__bytes_write.sum"), "source": f"profiles/{rnd}{tag}_fused_ncu.txt",
+             "kernel": "fx::fused4096::fused_kernel_stag<0, false>", "units_per_launch": "550 block pairs",
+             "fma_pipe_pct": float(m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][0].replace(",", "")),
+             "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0].replace(",", "")),
+             "registers": int(float(m["launch__registers_per_thread"][0].replace(",", "")))}
+    if step_dram:
+        facts["step_dram_bytes"] = step_dram
+        facts["step_dram_source"] = f"profiles/{rnd}{tag}_launches.csv (byte sums + fused + finalize)"
+    json.dump(facts, open(os.path.join(P, "fused_traffic.json"), "w"), indent=1)
 
 # ---- SASS listings -------------------------------------------------------------
 lib = os.path.join(ROOT, "effex_b200", "libeffex_fx.so")
@@ -111,4 +136,22 @@ if os.path.exists(lib):
             fh.write(f"// {d}\n// cuobjdump -sass effex_b200/libeffex_fx.so (sm_100a)\n")
             fh.write("\n".join(body) + "\n")
     print("sass:", len(out), "kernels")
+    # static FMA-pipe instruction counts of the fused kernel (bench.py's fp32_pipe view): packed = FFMA2/FADD2/FMUL2
+    # (2 issue cycles of the pipe per warp), scalar = FFMA/FADD/FMUL.  Whole kernel: the loop body executes
+    # once per frame and thread, the prologue/epilogue instructions (a few per cent) once per segment.
+    counts = {}
+    for (mangled, body), dname in zip(out.items(), dem):
+        for key, pat in (("no_autos", "fused_kernel_stag<0, false>"), ("autos", "fused_kernel_stag<0, true>")):
+            if pat in dname.replace("(bool)0", "false").replace("(bool)1", "true").replace("(int)0", "0"):
+                text = "\n".join(body)
+                counts[key] = {"packed": len(re.findall(r"\b(FFMA2|FADD2|FMUL2)\b", text)),
+                               "scalar": len(re.findall(r"\b(FFMA|FADD|FMUL)\b", text)),
+                               "sttm": len(re.findall(r"\bSTTM\b", text)), "ldtm": len(re.findall(r"\bLDTM\b", text)),
+                               "ublkcp": len(re.findall(r"\bUBLKCP\b", text))}
+    fj = os.path.join(P, "fused_traffic.json")
+    if counts and os.path.exists(fj):
+        facts = json.load(open(fj))
+        facts["sass_static_counts"] = counts
+        json.dump(facts, open(fj, "w"), indent=1)
+        print("sass counts:", counts)
 print("profiles written")
