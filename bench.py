@@ -294,8 +294,29 @@ def leg_c5(torch, synth, FxEngine, device, peak):
     text = csvio.format_rows(rows)
     t_csv = time.perf_counter() - t0
     eng.close()
+    # the whole command line on the same workload: interpreter start, imports, calibration, 6009 rows through
+    # fx_process_host, CSV formatted and written by the writer thread (synthetic input presented as views)
+    cli = None
+    try:
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            t0 = time.perf_counter()
+            res = subprocess.run([sys.executable, "-m", "effex_b200", "--time", "600", "--bandwidth", "3.2e6",
+                                  "--resolution", "1024", "--num_samp", "319488", "--extended", "--omit_plot", "1",
+                                  "--loglevel", "ERROR", "--timing", "--output", os.path.join(td, "c5.csv")],
+                                 capture_output=True, text=True, cwd=ROOT, timeout=300)
+            wall = time.perf_counter() - t0
+        for line in res.stdout.splitlines():
+            if line.startswith("{") and "effex_b200_cli_timing" in line:
+                cli = dict(json.loads(line)["effex_b200_cli_timing"], wall_s=wall,
+                           command="python -m effex_b200 --time 600 --bandwidth 3.2e6 --resolution 1024 --num_samp 319488 --extended --omit_plot 1")
+        if cli is None:
+            cli = {"error": (res.stderr or res.stdout)[-300:]}
+    except Exception as e:
+        cli = {"error": f"{type(e).__name__}: {e}"}
     alg = nb * (4 * S5 + 8 * N5)
     return {"workload": "configs[4]: bw=3.2e6 resolution=1024 integrations of 319488 samples, 6000 rows (600 distinct x 10)",
+            "cli": cli,
             "value": nb * S5 / t_dev / 1e6, "unit": UNIT, "ms_per_600_rows": t_dev * 1e3,
             "dominant_kernel": "fx::fused4096::fused_kernel_stag<2>", "dominant_kernel_ms": kms / max(kn, 1),
             "algorithmic_bytes": alg, "bytes_per_pair_sample": alg / (nb * S5), "frac": alg / t_dev / 1e9 / peak,

@@ -45,13 +45,17 @@ def build_parser() -> argparse.ArgumentParser:
                         help='lift the reference clamp num_samp <= 2^18 (BASELINE configs 3 and 5)')
     parser.add_argument('--device', default=0, type=int)
     parser.add_argument('--output', default=None, help='csv path (default visibilities_%%Y%%m%%d-%%H%%M%%S.csv)')
+    parser.add_argument('--timing', action='store_true', help='print a JSON line with the wall time of each phase')
     return parser
 
 
 def main(argv=None):
+    import time
+    t_start = time.perf_counter()
     args = build_parser().parse_args(argv)
     from .correlator import Correlator
     from . import synth, csvio
+    phases = {"import_s": time.perf_counter() - t_start}
     cor = Correlator(run_time=args.run_time, bandwidth=args.bandwidth, frequency=args.fc, num_samp=args.num_samp,
                      nbins=args.nfft, gain=args.gain, mode=args.mode, loglevel=args.loglevel, device=args.device,
                      extended=args.extended, output_file=args.output)
@@ -66,10 +70,22 @@ def main(argv=None):
             raw0 = np.fromfile(args.input0, dtype=np.uint8, count=2 * S * n_blocks)
             raw1 = np.fromfile(args.input1, dtype=np.uint8, count=2 * S * n_blocks)
         else:
-            raw0, raw1 = synth.tiled_recording(n_blocks, S, base_blocks=min(8, n_blocks), delay=args.synthetic_delay)
+            # synthetic recording: 8 fresh blocks repeated, presented as views (an hour of data is 17 GB per channel)
+            raw0, raw1 = synth.tiled_recording_lazy(n_blocks, S, base_blocks=min(8, n_blocks), delay=args.synthetic_delay,
+                                                    window_blocks=cor.batch_blocks)
+        phases["input_s"] = time.perf_counter() - t_start - phases["import_s"]
+        t_run = time.perf_counter()
         cor.run_recording(raw0, raw1)
+        phases["run_s"] = time.perf_counter() - t_run
     cor.close()
     print(f'wrote {cor.output_file}; estimated delay {1e6 * cor.calibrated_delay:.6f} us')
+    if args.timing:
+        import json
+        import os
+        phases["total_s"] = time.perf_counter() - t_start
+        phases["csv_bytes"] = os.path.getsize(cor.output_file)
+        phases["rows"] = max(n_blocks - 1, 0)
+        print(json.dumps({"effex_b200_cli_timing": phases}))
     if not args.omit_plot:
         try:
             import matplotlib  # noqa: F401

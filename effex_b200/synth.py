@@ -85,3 +85,50 @@ def tiled_recording(n_blocks: int, num_samp: int, base_blocks: int = 8, delay: i
     raw0 = np.tile(base0, reps)[: 2 * num_samp * n_blocks]
     raw1 = np.tile(base1, reps)[: 2 * num_samp * n_blocks]
     return raw0, raw1
+
+
+class TiledRecording:
+    """A long recording that is `base_blocks` fresh blocks repeated (like tiled_recording) WITHOUT being
+    materialised: contiguous slices are views into a window of the periodic pattern, so a one-hour
+    recording (17 GB per channel) costs `window_blocks + base_blocks` blocks of (pinned, when CUDA is there)
+    host memory.  Supports what Correlator.run_recording needs: `.size`, and `rec[lo:hi]` with hi - lo up to
+    window_blocks blocks."""
+
+    def __init__(self, base: np.ndarray, n_blocks: int, num_samp: int, window_blocks: int = 64):
+        self.block_bytes = 2 * int(num_samp)
+        self.period = base.size
+        if self.period % self.block_bytes:
+            raise ValueError("base must hold whole blocks")
+        self.size = self.block_bytes * int(n_blocks)
+        self.dtype = base.dtype
+        reps = -(-(window_blocks * self.block_bytes + self.period) // self.period) + 1
+        buf = np.tile(base, reps)
+        try:
+            import torch
+            if torch.cuda.is_available():
+                pinned = torch.empty(buf.size, dtype=torch.uint8).pin_memory().numpy()
+                pinned[:] = buf
+                buf = pinned
+        except Exception:
+            pass
+        self._buf = buf
+
+    def __len__(self):
+        return self.size
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice) or key.step not in (None, 1):
+            raise TypeError("TiledRecording supports contiguous slices only")
+        lo, hi, _ = key.indices(self.size)
+        off = lo % self.period
+        if off + (hi - lo) > self._buf.size:
+            raise ValueError("slice longer than the window this recording was built with")
+        return self._buf[off:off + max(hi - lo, 0)]
+
+
+def tiled_recording_lazy(n_blocks: int, num_samp: int, base_blocks: int = 8, delay: int = 37, seed: int = SEED,
+                         window_blocks: int = 64):
+    """tiled_recording as two TiledRecording views (same bytes, no multi-GB copies)."""
+    base0, base1 = correlated_pair(base_blocks * num_samp, delay=delay, seed=seed)
+    return (TiledRecording(base0, n_blocks, num_samp, window_blocks),
+            TiledRecording(base1, n_blocks, num_samp, window_blocks))

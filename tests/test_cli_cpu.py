@@ -17,3 +17,17 @@ def test_flags_match_reference():
         except SystemExit:
             continue
         raise AssertionError(bad)
+
+
+def test_lazy_tiled_recording_is_the_tiled_recording():
+    import numpy as np
+    from effex_b200 import synth
+    S = 1024
+    a0, a1 = synth.tiled_recording(37, S, base_blocks=8, delay=3)
+    b0, b1 = synth.tiled_recording_lazy(37, S, base_blocks=8, delay=3, window_blocks=5)
+    assert b0.size == a0.size and len(b1) == a1.size
+    for lo, hi in ((0, 2 * S), (2 * S * 3, 2 * S * 8), (2 * S * 30, 2 * S * 35), (2 * S * 36, 2 * S * 37), (2 * S * 7, 2 * S * 12)):
+        assert np.array_equal(a0[lo:hi], b0[lo:hi]) and np.array_equal(a1[lo:hi], b1[lo:hi])
+    import pytest
+    with pytest.raises(ValueError):
+        b0[0:2 * S * 37]                       # longer than the window
