@@ -90,6 +90,11 @@ struct fx_handle {
     float2 *d_g0 = nullptr, *d_g1 = nullptr, *d_gtmp = nullptr;   // generic-path frame buffers
     size_t g_cap = 0;                                             // elements per buffer
 
+    // Bluestein (nbins not a power of two): chirp c[n], B = FFT_M(conj chirp), work buffers [rows][M]
+    bool bluestein = false;
+    int bsM = 0;
+    float2 *d_bs_chirp = nullptr, *d_bs_B = nullptr, *d_bs_a = nullptr, *d_bs_tmp = nullptr;
+    long long bs_rows = 0;
     float2 *d_lag_rows = nullptr, *d_lag_tmp = nullptr, *d_lag_acc = nullptr, *d_lag_acc_tmp = nullptr;
     long long lagM = 0;
     bool lag_fast = false;                     // M = G*4096, G in [2, 256]: head/tail kernels (fx_lag.cuh)
@@ -673,7 +678,7 @@ int ensure_generic(fx_handle *h, size_t elems) {
 __global__ void phase_post_kernel(float2 *x, int N, long long total) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int c = (int)(i & (N - 1));
+    const int c = (int)(i % N);
     float sn, cs;
     sincospif(-2.f * (float)c / (float)N, &sn, &cs);
     const float2 v = x[i];
@@ -710,7 +715,37 @@ int stockham_passes(fx_handle *h, float2 *buf, float2 *tmp, long long M, long lo
 // batched FFT of `rows` rows of length N held in buf; tmp is scratch of the same size.
 // Result is left in buf.
 int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, int inverse, int phase_post,
+                bool timed);
+
+// N-point forward DFT of `rows` rows for any N (Bluestein), in chunks of bs_rows rows through [rows][M] buffers
+int fft_bluestein(fx_handle *h, float2 *buf, int N, long long rows, int phase_post, bool timed) {
+    const int M = h->bsM;
+    EventPair ep{};
+    int rc = timed ? begin_timed(h, ep) : FX_OK;
+    if (rc) return rc;
+    for (long long r0 = 0; r0 < rows; r0 += h->bs_rows) {
+        const long long nr = std::min<long long>(h->bs_rows, rows - r0);
+        dim3 gm((M + 255) / 256, (unsigned)nr), gn((N + 255) / 256, (unsigned)nr);
+        fx::generic::bluestein_pre_kernel<<<gm, 256, 0, h->stream>>>(buf + r0 * N, h->d_bs_chirp, N, M, h->d_bs_a);
+        FX_LAUNCH_CHECK(h, "bluestein_pre");
+        rc = fft_batched(h, h->d_bs_a, h->d_bs_tmp, M, nr, 0, 0, false);
+        if (rc) return rc;
+        fx::generic::bluestein_mul_kernel<<<gm, 256, 0, h->stream>>>(h->d_bs_a, h->d_bs_B, M);
+        FX_LAUNCH_CHECK(h, "bluestein_mul");
+        rc = fft_batched(h, h->d_bs_a, h->d_bs_tmp, M, nr, 1, 0, false);
+        if (rc) return rc;
+        fx::generic::bluestein_post_kernel<<<gn, 256, 0, h->stream>>>(h->d_bs_a, h->d_bs_chirp, N, M, phase_post, buf + r0 * N);
+        FX_LAUNCH_CHECK(h, "bluestein_post");
+    }
+    return timed ? end_timed(h, ep) : FX_OK;
+}
+
+int fft_batched(fx_handle *h, float2 *buf, float2 *tmp, int N, long long rows, int inverse, int phase_post,
                 bool timed) {
+    if (!is_pow2(N)) {
+        if (inverse || N != h->cfg.nbins || !h->bluestein) return fail(h, FX_ERR_UNSUPPORTED, "inverse / foreign-length Bluestein transform");
+        return fft_bluestein(h, buf, N, rows, phase_post, timed);
+    }
     const int logN = ilog2(N);
     EventPair ep{};
     int rc = timed ? begin_timed(h, ep) : FX_OK;
@@ -840,7 +875,7 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
     if (rc) return rc;
     if (sink.any()) {
         // the fold of the per-group sums rides in the tail of the kernel that produces them (comm::integrate_tail)
-        const bool can_tail = N >= 256 && (N % 256) == 0;
+        const bool can_tail = N >= 256 && is_pow2(N);
         fx::comm::IntegrateTail tail;
         memset(&tail, 0, sizeof(tail));
         int use_tail = 0;
@@ -1231,8 +1266,8 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     if (cfg->ntaps < 1) return fail(nullptr, FX_ERR_INVALID, "ntaps must be >= 1");
     if (cfg->ntaps > fx::kMaxTaps)
         return fail(nullptr, FX_ERR_UNSUPPORTED, "ntaps > 32 is not supported (cuSignal channelize_poly has the same cap)");
-    if (!is_pow2(cfg->nbins) || cfg->nbins < 8 || cfg->nbins > 65536)
-        return fail(nullptr, FX_ERR_UNSUPPORTED, "nbins must be a power of two in [8, 65536]");
+    if (cfg->nbins < 8 || cfg->nbins > 65536)
+        return fail(nullptr, FX_ERR_UNSUPPORTED, "nbins must be in [8, 65536]");
     if (cfg->num_samp < 1) return fail(nullptr, FX_ERR_INVALID, "num_samp must be >= 1");
     if (cfg->num_samp / cfg->nbins < 1)
         return fail(nullptr, FX_ERR_INVALID, "there must be at least one frame of nbins samples per block");
@@ -1256,10 +1291,11 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
     h->P = (int)(cfg->num_samp / cfg->nbins);
     h->logN = ilog2(cfg->nbins);
     h->num_sms = prop.multiProcessorCount;
-    h->fused = cfg->nbins >= 256 && cfg->nbins <= fx::fused4096::N && cfg->ntaps == fx::fused4096::T &&
+    h->bluestein = !is_pow2(cfg->nbins);
+    h->fused = !h->bluestein && cfg->nbins >= 256 && cfg->nbins <= fx::fused4096::N && cfg->ntaps == fx::fused4096::T &&
                (cfg->num_samp % 8) == 0 && !(cfg->flags & FX_FLAG_FORCE_GENERIC);
     h->logF = h->fused ? 12 - h->logN : 0;
-    h->big = cfg->nbins > fx::fused4096::N && cfg->nbins <= 65536 && cfg->ntaps == fx::fused4096::T &&
+    h->big = !h->bluestein && cfg->nbins > fx::fused4096::N && cfg->nbins <= 65536 && cfg->ntaps == fx::fused4096::T &&
              !(cfg->flags & FX_FLAG_FORCE_GENERIC);
     h->logG = h->big ? h->logN - 12 : 0;
     auto bail = [&](const std::string &m) { g_create_error = m; fx_destroy(h); return FX_ERR_CUDA; };
@@ -1309,6 +1345,50 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         const size_t tiles = std::max<size_t>(1, (size_t)cfg->nbins / 256);
         CREATE_CUDA(cudaMalloc(&h->d_tile_counters, tiles * sizeof(int)));
         CREATE_CUDA(cudaMemset(h->d_tile_counters, 0, tiles * sizeof(int)));
+    }
+    if (h->bluestein) {
+        // chirp c[n] = exp(-i pi n^2 / N) (n^2 mod 2N in integers) and B = FFT_M of the wrapped conjugate chirp,
+        // both in float64 on the host
+        const int N = cfg->nbins;
+        int M = 1;
+        while (M < 2 * N - 1) M <<= 1;
+        h->bsM = M;
+        std::vector<double> cr(N), ci(N), br(M, 0.0), bi(M, 0.0);
+        for (int n = 0; n < N; ++n) {
+            const long long q = ((long long)n * n) % (2ll * N);
+            const double a = -M_PI * (double)q / (double)N;
+            cr[n] = cos(a); ci[n] = sin(a);
+            br[n] = cr[n]; bi[n] = -ci[n];
+            if (n) { br[M - n] = cr[n]; bi[M - n] = -ci[n]; }
+        }
+        // iterative radix-2 FFT of length M (decimation in time), float64
+        for (int i = 1, j = 0; i < M; ++i) {
+            int bit = M >> 1;
+            for (; j & bit; bit >>= 1) j ^= bit;
+            j ^= bit;
+            if (i < j) { std::swap(br[i], br[j]); std::swap(bi[i], bi[j]); }
+        }
+        for (int len = 2; len <= M; len <<= 1) {
+            const double ang = -2.0 * M_PI / len;
+            for (int i = 0; i < M; i += len)
+                for (int k = 0; k < len / 2; ++k) {
+                    const double wr = cos(ang * k), wi = sin(ang * k);
+                    const int u = i + k, v = i + k + len / 2;
+                    const double xr = br[v] * wr - bi[v] * wi, xi = br[v] * wi + bi[v] * wr;
+                    br[v] = br[u] - xr; bi[v] = bi[u] - xi;
+                    br[u] += xr; bi[u] += xi;
+                }
+        }
+        std::vector<float2> chirp(N), B(M);
+        for (int n = 0; n < N; ++n) chirp[n] = make_float2((float)cr[n], (float)ci[n]);
+        for (int m = 0; m < M; ++m) B[m] = make_float2((float)br[m], (float)bi[m]);
+        CREATE_CUDA(cudaMalloc(&h->d_bs_chirp, N * sizeof(float2)));
+        CREATE_CUDA(cudaMalloc(&h->d_bs_B, M * sizeof(float2)));
+        CREATE_CUDA(cudaMemcpy(h->d_bs_chirp, chirp.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(h->d_bs_B, B.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+        h->bs_rows = std::max<long long>(1, std::min<long long>(65535, (1ll << 24) / M));      // 128 MiB per work buffer
+        CREATE_CUDA(cudaMalloc(&h->d_bs_a, (size_t)h->bs_rows * M * sizeof(float2)));
+        CREATE_CUDA(cudaMalloc(&h->d_bs_tmp, (size_t)h->bs_rows * M * sizeof(float2)));
     }
     CREATE_CUDA(cudaFuncSetAttribute(fx::generic::fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      3 * 4096 * (int)sizeof(float2)));
@@ -1389,7 +1469,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_bs_chirp, h->d_bs_B, h->d_bs_a, h->d_bs_tmp, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

@@ -392,6 +392,55 @@ __global__ void __launch_bounds__(256) xengine_kernel(const float2 *__restrict__
     part_a[(long long)b * N + c] = make_float2(a0, a1);
 }
 
+// np.fft.fftshift for any N: out[j] = X[(j + ceil(N/2)) mod N]
+__device__ __forceinline__ int shifted_bin(int j, int N) {
+    const int c = j + ((N + 1) >> 1);
+    return c >= N ? c - N : c;
+}
+
+// ---------------------------------------------------------------------------
+// Bluestein: the N-point DFT of any N as a circular convolution of length M = 2^m >= 2N - 1
+// (the reference takes any --resolution through cuFFT, effex.py:553, :734):
+//   X[k] = c[k] * sum_n (x[n] c[n]) * conj(c)[k - n],   c[n] = exp(-i pi n^2 / N)
+// pre: a[r][n] = x[r][n] * c[n] (n < N), 0 (N <= n < M); then FFT_M, times B = FFT_M(conj chirp, wrapped),
+// inverse FFT_M, post: X[r][k] = c[k] * a[r][k] / M (times exp(-2 pi i k / N) when phase_post).
+// The chirp and B are built on the host in float64 (n^2 mod 2N in integers).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bluestein_pre_kernel(const float2 *__restrict__ x, const float2 *__restrict__ chirp,
+                                                            int N, int M, float2 *__restrict__ a) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (m >= M) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (m < N) {
+        const float2 q = x[r * N + m], c = chirp[m];
+        v = make_float2(q.x * c.x - q.y * c.y, q.x * c.y + q.y * c.x);
+    }
+    a[r * M + m] = v;
+}
+__global__ void __launch_bounds__(256) bluestein_mul_kernel(float2 *__restrict__ a, const float2 *__restrict__ B, int M) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (m >= M) return;
+    const float2 q = a[r * M + m], b = B[m];
+    a[r * M + m] = make_float2(q.x * b.x - q.y * b.y, q.x * b.y + q.y * b.x);
+}
+__global__ void __launch_bounds__(256) bluestein_post_kernel(const float2 *__restrict__ a, const float2 *__restrict__ chirp,
+                                                             int N, int M, int phase_post, float2 *__restrict__ x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    if (k >= N) return;
+    const float inv = 1.0f / (float)M;
+    const float2 q = a[r * M + k], c = chirp[k];
+    float2 v = make_float2((q.x * c.x - q.y * c.y) * inv, (q.x * c.y + q.y * c.x) * inv);
+    if (phase_post) {
+        float sn, cs;
+        sincospif(-2.f * (float)k / (float)N, &sn, &cs);
+        v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+    }
+    x[r * N + k] = v;
+}
+
 // ---------------------------------------------------------------------------
 // finalize: rows in the reference's output order (effex.py:519-521):
 //   out[b][j] = conj(rot[c]) * (1/P) * sum_{s in segments of block b} part_x[s][c],  c = (j + N/2) mod N
@@ -407,7 +456,7 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(const float2 *__rest
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = block0 + blockIdx.y;
     if (j >= N) return;
-    const int c = (j + (N >> 1)) & (N - 1);
+    const int c = shifted_bin(j, N);
     const int s0 = blk_first ? blk_first[b] : b;
     const int s1 = blk_first ? blk_first[b + 1] : b + 1;
     float xr = 0.f, xi = 0.f, a0 = 0.f, a1 = 0.f;
@@ -447,7 +496,7 @@ __global__ void __launch_bounds__(256, FX_FIN_CTAS) finalize_integrate_kernel(co
     constexpr bool autos = AUTOS;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = j < N;
-    const int c = (j + (N >> 1)) & (N - 1);
+    const int c = shifted_bin(j, N);
     const int G = gridDim.y, g = blockIdx.y;
     if (valid) {
         const int b0 = (int)((long long)n_blocks * g / G), b1 = (int)((long long)n_blocks * (g + 1) / G);

@@ -53,7 +53,8 @@ typedef struct fx_handle fx_handle;
 typedef struct {
     int32_t device;       /* CUDA device ordinal                                           */
     int32_t ntaps;        /* T, PFB taps per branch (effex.py:115 uses 4; cuSignal cap 32) */
-    int32_t nbins;        /* N = --resolution, power of two, 8..65536                      */
+    int32_t nbins;        /* N = --resolution, 8..65536; any integer (effex.py:734 takes any: cuFFT);
+                             powers of two run the fused kernels, others the unfused ones + Bluestein */
     int32_t dc_remove;    /* 1: per-block DC removal of effex.py:394-395; 0: none          */
     int64_t num_samp;     /* S complex samples per block (effex.py:87, --num_samp)         */
     int32_t max_blocks;   /* capacity: blocks per fx_process / fx_integrate call           */

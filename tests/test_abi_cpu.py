@@ -42,8 +42,9 @@ def test_argument_validation_needs_no_gpu():
     h = C.c_void_p()
     bad = _lib.FxConfig(0, 33, 4096, 1, 2**18, 1, 0)       # ntaps > 32, like cuSignal's cap
     assert lib.fx_create(C.byref(bad), C.byref(h)) == _lib.FX_ERR_UNSUPPORTED
-    bad = _lib.FxConfig(0, 4, 3000, 1, 2**18, 1, 0)        # nbins not a power of two
-    assert lib.fx_create(C.byref(bad), C.byref(h)) == _lib.FX_ERR_UNSUPPORTED
+    for nb in (7, 65537):                                  # nbins outside [8, 65536] (any integer inside is fine)
+        bad = _lib.FxConfig(0, 4, nb, 1, 2**18, 1, 0)
+        assert lib.fx_create(C.byref(bad), C.byref(h)) == _lib.FX_ERR_UNSUPPORTED
     bad = _lib.FxConfig(0, 4, 4096, 1, 100, 1, 0)          # less than one frame
     assert lib.fx_create(C.byref(bad), C.byref(h)) == _lib.FX_ERR_INVALID
     assert b"frame" in lib.fx_last_error(None)

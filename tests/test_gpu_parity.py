@@ -379,7 +379,7 @@ def test_errors_are_value_errors():
     with pytest.raises(ValueError):
         FxEngine(2**18, 4096, 33)
     with pytest.raises(ValueError):
-        FxEngine(2**18, 3000, 4)
+        FxEngine(2**18, 70000, 4)              # nbins outside [8, 65536]
     eng = FxEngine(2**14, 1024, 4, max_blocks=1)
     raw = torch.zeros(4 * 2**14, dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
