@@ -176,21 +176,51 @@ int fx_csv_format_rows(const float *h_rows, int64_t n_rows, int64_t nbins, int n
                        size_t out_cap, size_t *out_len) {
     if (!h_rows || !h_out || !out_len || n_rows < 0 || nbins < 1) return FX_ERR_INVALID;
     if (out_cap < fx_csv_rows_bound(n_rows, nbins)) return FX_ERR_INVALID;
-    const size_t stride = (size_t)nbins * kElemMax + 2;
     if (n_threads < 1) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads < 1) n_threads = 1;
     if ((int64_t)n_threads > n_rows) n_threads = (int)(n_rows > 0 ? n_rows : 1);
+    auto run = [&](auto &&work) {
+        std::vector<std::thread> pool;
+        for (int i = 1; i < n_threads; ++i) pool.emplace_back(work, i);
+        work(0);
+        for (auto &t : pool) t.join();
+    };
+    // A finite float32 prints with a two-digit exponent, so an element is 53 characters plus one per minus
+    // sign of the real part: the row lengths are known before a digit is produced and every row is formatted
+    // straight into its final place.  (Rows holding inf/nan take the slot path below.)
     std::vector<size_t> len((size_t)n_rows, 0);
-    // pass 1: every row into its own worst-case slot, in parallel
-    auto work = [&](int tid) {
+    std::vector<char> odd((size_t)n_threads, 0);
+    run([&](int tid) {
+        for (int64_t r = tid; r < n_rows; r += n_threads) {
+            const float *row = h_rows + 2 * (size_t)nbins * (size_t)r;
+            size_t neg = 0;
+            bool finite = true;
+            for (int64_t c = 0; c < nbins; ++c) {
+                neg += std::signbit(row[2 * c]) ? 1 : 0;
+                finite = finite && std::isfinite(row[2 * c]) && std::isfinite(row[2 * c + 1]);
+            }
+            if (!finite) odd[(size_t)tid] = 1;
+            len[(size_t)r] = (size_t)nbins * 53 + neg + (size_t)(nbins - 1) + 1;
+        }
+    });
+    bool any_odd = false;
+    for (char o : odd) any_odd = any_odd || o;
+    if (!any_odd) {
+        std::vector<size_t> off((size_t)n_rows + 1, 0);
+        for (int64_t r = 0; r < n_rows; ++r) off[(size_t)r + 1] = off[(size_t)r] + len[(size_t)r];
+        run([&](int tid) {
+            for (int64_t r = tid; r < n_rows; r += n_threads)
+                format_row(h_rows + 2 * (size_t)nbins * (size_t)r, nbins, h_out + off[(size_t)r]);
+        });
+        *out_len = off[(size_t)n_rows];
+        return FX_OK;
+    }
+    // general path: every row into its own worst-case slot in parallel, then compacted in row order
+    const size_t stride = (size_t)nbins * kElemMax + 2;
+    run([&](int tid) {
         for (int64_t r = tid; r < n_rows; r += n_threads)
             len[(size_t)r] = format_row(h_rows + 2 * (size_t)nbins * (size_t)r, nbins, h_out + stride * (size_t)r);
-    };
-    std::vector<std::thread> pool;
-    for (int i = 1; i < n_threads; ++i) pool.emplace_back(work, i);
-    work(0);
-    for (auto &t : pool) t.join();
-    // pass 2: compact in row order (memmove: slots never overlap their packed destination from behind)
+    });
     size_t off = 0;
     for (int64_t r = 0; r < n_rows; ++r) {
         memmove(h_out + off, h_out + stride * (size_t)r, len[(size_t)r]);

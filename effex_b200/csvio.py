@@ -39,6 +39,32 @@ def format_rows_py(rows) -> str:
     return '\n'.join(out) + '\n'
 
 
+_scratch = None          # per-thread reusable output buffer (no 34 MB zero-fill and no extra copies per batch)
+
+
+def _format_rows_view(rows, n_threads: int = 0):
+    """complex64 rows -> a uint8 numpy VIEW of the formatted text (valid until the calling thread's next
+    call): the library writes into a reusable buffer and nothing is copied on the Python side."""
+    import ctypes as C
+    import threading
+    from . import _lib
+    global _scratch
+    if _scratch is None:
+        _scratch = threading.local()
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows)
+    n_rows, nbins = rows.shape
+    cap = lib.fx_csv_rows_bound(n_rows, nbins)
+    buf = getattr(_scratch, "buf", None)
+    if buf is None or buf.size < cap:
+        buf = _scratch.buf = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    rc = lib.fx_csv_format_rows(rows.ctypes.data, n_rows, nbins, n_threads, buf.ctypes.data, buf.size, C.byref(n))
+    if rc != 0:
+        raise ValueError(f"fx_csv_format_rows failed ({rc})")
+    return buf[:n.value]
+
+
 def format_rows(rows, n_threads: int = 0) -> bytes:
     """complex64 rows -> the bytes np.savetxt would write, through the library's parallel C
     formatter (fx_csv_format_rows).  Other dtypes fall back to the Python formatter."""
@@ -47,23 +73,23 @@ def format_rows(rows, n_threads: int = 0) -> bytes:
         rows = rows.reshape(1, -1)
     if rows.dtype != np.complex64:
         return format_rows_py(rows).encode()
-    import ctypes as C
-    from . import _lib
-    lib = _lib.load()
-    rows = np.ascontiguousarray(rows)
-    n_rows, nbins = rows.shape
-    cap = lib.fx_csv_rows_bound(n_rows, nbins)
-    buf = C.create_string_buffer(cap)
-    n = C.c_size_t()
-    rc = lib.fx_csv_format_rows(rows.ctypes.data, n_rows, nbins, n_threads, buf, cap, C.byref(n))
-    if rc != 0:
-        raise ValueError(f"fx_csv_format_rows failed ({rc})")
-    return buf.raw[:n.value]
+    return _format_rows_view(rows, n_threads).tobytes()
+
+
+def write_rows(fh, rows, n_threads: int = 0):
+    """format + write without an intermediate bytes object"""
+    rows = np.asarray(rows)
+    if rows.ndim == 1:
+        rows = rows.reshape(1, -1)
+    if rows.dtype != np.complex64:
+        fh.write(format_rows_py(rows).encode())
+    else:
+        fh.write(memoryview(_format_rows_view(rows, n_threads)))
 
 
 def append_rows(path, rows):
     with open(path, 'ab') as fh:
-        fh.write(format_rows(rows))
+        write_rows(fh, rows)
 
 
 class RowWriter:
@@ -88,7 +114,7 @@ class RowWriter:
                     if rows is None:
                         return
                     if self.error is None:
-                        fh.write(format_rows(rows))
+                        write_rows(fh, rows)
         except Exception as e:          # keep draining so that put() never blocks forever
             self.error = e
             while self.q.get() is not None:
