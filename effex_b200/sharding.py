@@ -45,8 +45,21 @@ def attach_comm(engine, group=None, slot_bytes: int = 0) -> bool:
     mine = torch.frombuffer(bytearray(tok), dtype=torch.uint8).to(engine.tdev)
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine, group=group)
-    engine.comm_attach(rank, world, [bytes(g.cpu().numpy().tobytes()) for g in gathered])
-    dist.barrier(group=group)          # every rank has mapped every mailbox before anyone pushes
+    ok = 1
+    try:
+        import os
+        if os.environ.get("EFFEX_FX_NO_IPC"):          # test hook: behave like a box that refuses CUDA IPC
+            raise RuntimeError("EFFEX_FX_NO_IPC is set")
+        engine.comm_attach(rank, world, [bytes(g.cpu().numpy().tobytes()) for g in gathered])
+    except Exception as e:             # e.g. CUDA IPC not permitted between these processes
+        ok = 0
+        engine.comm_error = str(e)
+    # all ranks or none: a rank that could not map its peers takes everybody back to dist.reduce
+    flag = torch.tensor([ok], dtype=torch.int32, device=engine.tdev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        engine.comm_world = 0
+        return False
     return True
 
 
