@@ -490,12 +490,15 @@ def run_ours(args):
     max_ms = float(t.item())
     value = world * N_BLOCKS * S * args.steps / (max_ms * 1e-3) / 1e6
 
-    # the same load kept up for ~1 s (not timed) so that the clock record has enough samples
+    # the same load kept up for ~1 s (not timed) so that the clock record has enough samples.  The number of
+    # steps comes from the all-reduced step time, so every rank makes the same number of collective calls
+    n_load = int(min(5000, max(100, 1.0 / (max_ms / args.steps * 1e-3))))
     t_load0 = time.time()
-    while time.time() - t_load0 < 1.0:
-        for _ in range(50):
-            step()
-        eng.sync()
+    for i in range(n_load):
+        step()
+        if i % 50 == 49:
+            eng.sync()
+    eng.sync()
     t_load1 = time.time()
     barrier()
     clocks = None
