@@ -126,7 +126,7 @@ struct fx_handle {
         // the root folds epoch e one collective call later (or in fx_comm_fence / fx_sync): by then the
         // peers' pushes of epoch e have had a whole step to land, so the fold hardly ever spins
         struct Pending { unsigned int epoch = 0; void *dst = nullptr; size_t n = 0; int accumulate = 0; bool f64 = true; } pending;
-        long long timeout_cycles = 20000000000ll;    // ~10 s at 1.965 GHz
+        long long timeout_cycles = 60000000000ll;    // ~30 s at 1.965 GHz
         double *d_acc_local = nullptr;               // [4N+1] staging for paths that run several stage-2 passes per call
     } comm;
 

@@ -154,7 +154,7 @@ int fx_integrate_stream(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1
  *   fx_reduce_f64/f32  in-place sum of d_buf[n] over the ranks into the root's d_buf (collective; the lag
  *                    search reduces its accumulated 2n-point cross-spectrum with it); folded at once on
  *                    fx_stream().  (One host thread driving several ranks must call the root last.)
- * A rank that waits ~10 s for a peer gives up and the next fx_sync() returns FX_ERR_COMM. All ranks must
+ * A rank that waits ~30 s for a peer gives up and the next fx_sync() returns FX_ERR_COMM. All ranks must
  * fx_sync() (and the host must barrier) before any of them destroys its handle.                           */
 #define FX_COMM_TOKEN_BYTES 128
 int fx_comm_export(fx_handle *h, int world, size_t slot_bytes, void *h_token);
