@@ -34,19 +34,33 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
-    """`defines`/`out` build an experiment variant (tools/kbench.py); the product is the default."""
+    """`defines`/`out` build an experiment variant (tools/kbench.py); the product is the default.
+    Safe against concurrent callers (the ranks of a torchrun launch): one builds under an exclusive lock into a
+    temporary file that is renamed into place, the others wait and find a fresh library."""
     if out is None and not force and not _stale():
         return LIB
     out = out or LIB
-    cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-pthread", "-shared",
-           "-o", out] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libeffex_fx.so")
+    import fcntl
+    with open(out + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out == LIB and not force and not _stale():        # somebody else built it while we waited
+                return LIB
+            tmp = f"{out}.tmp{os.getpid()}"
+            cmd = [_nvcc(), "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-pthread", "-shared",
+                   "-o", tmp] + [f"-D{d}" for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libeffex_fx.so")
+            os.replace(tmp, out)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
 
 
