@@ -102,8 +102,8 @@ def load() -> C.CDLL:
         try:
             if _build._stale():
                 _build.build()
-        except RuntimeError:
-            pass                               # no nvcc: the ABI version check below is the guard
+        except Exception:                      # no nvcc, read-only tree, ...: the ABI version check below is the guard
+            pass
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:                       # pragma: no cover - environment specific
