@@ -221,8 +221,8 @@ __device__ __forceinline__ void integrate_tail(const IntegrateTail &t, const dou
         double *slot = reinterpret_cast<double *>(t.push.slot);
         if (valid) {
             *reinterpret_cast<double2 *>(slot + 2 * c) = make_double2(v0, v1);
-            slot[2 * N + c] = t.autos ? v2 : 0.0;
-            slot[3 * N + c] = t.autos ? v3 : 0.0;
+            // cross-only handles never write the auto-power parts of a slot: they stay zero from fx_comm_export
+            if (t.autos) { slot[2 * N + c] = v2; slot[3 * N + c] = v3; }
         }
         if (tile == 0 && threadIdx.x == 0) slot[4 * (size_t)N] = frames;
         __syncthreads();
@@ -240,16 +240,16 @@ __device__ __forceinline__ void integrate_tail(const IntegrateTail &t, const dou
         double *d = t.fold_dst;
         if (valid) {
             double2 ax = *reinterpret_cast<double2 *>(d + 2 * c);
-            double a0 = d[2 * N + c], a1 = d[3 * N + c];
+            double a0 = 0, a1 = 0;
+            if (t.autos) { a0 = d[2 * N + c]; a1 = d[3 * N + c]; }
             for (int r = 0; r < t.world; ++r) {
                 const double *sl = reinterpret_cast<const double *>(reinterpret_cast<const char *>(t.fold_slots) + (size_t)r * t.slot_stride_bytes);
                 const double2 x = __ldcg(reinterpret_cast<const double2 *>(sl + 2 * c));
                 ax.x += x.x; ax.y += x.y;
-                a0 += __ldcg(sl + 2 * N + c);
-                a1 += __ldcg(sl + 3 * N + c);
+                if (t.autos) { a0 += __ldcg(sl + 2 * N + c); a1 += __ldcg(sl + 3 * N + c); }
             }
             *reinterpret_cast<double2 *>(d + 2 * c) = ax;
-            d[2 * N + c] = a0; d[3 * N + c] = a1;
+            if (t.autos) { d[2 * N + c] = a0; d[3 * N + c] = a1; }
         }
         if (tile == 0 && threadIdx.x == 0) {
             double f = d[4 * (size_t)N];
