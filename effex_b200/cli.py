@@ -9,6 +9,7 @@ a synthetic correlated-noise recording).
 from __future__ import annotations
 
 import argparse
+import os
 
 import numpy as np
 
@@ -56,11 +57,17 @@ def main(argv=None):
     from .correlator import Correlator
     from . import synth, csvio
     phases = {"import_s": time.perf_counter() - t_start}
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))
     cor = Correlator(run_time=args.run_time, bandwidth=args.bandwidth, frequency=args.fc, num_samp=args.num_samp,
                      nbins=args.nfft, gain=args.gain, mode=args.mode, loglevel=args.loglevel, device=args.device,
                      extended=args.extended, output_file=args.output)
     S = int(cor.num_samp)
     n_blocks = int(np.ceil(cor.run_time * cor.bandwidth / S))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # launched with torchrun: one process per GPU, the blocks of the run time-sharded over the ranks
+        return _main_sharded(args, cor, n_blocks, world, phases, t_start)
     if args.input0 and args.input1 and args.mode != 'test':
         from .correlator import run_files
         # streamed in chunks of whole blocks; a FIFO / pipe ends at EOF or after --time worth of blocks
@@ -81,7 +88,6 @@ def main(argv=None):
     print(f'wrote {cor.output_file}; estimated delay {1e6 * cor.calibrated_delay:.6f} us')
     if args.timing:
         import json
-        import os
         phases["total_s"] = time.perf_counter() - t_start
         phases["csv_bytes"] = os.path.getsize(cor.output_file)
         phases["rows"] = max(n_blocks - 1, 0)
@@ -96,6 +102,47 @@ def main(argv=None):
         meta, rows = csvio.read_rows(cor.output_file)
         post_process(rows, args.bandwidth, args.fc, args.nfft, args.mode, args.omit_plot,
                      test_delay_sweep_step=cor.test_delay_sweep_step if args.mode == 'test' else 0)
+    return 0
+
+
+def _main_sharded(args, cor, n_blocks, world, phases, t_start):
+    """`torchrun --nproc-per-node N -m effex_b200 ...`: rank 0 calibrates and writes the CSV, every rank
+    correlates its own contiguous range of blocks (north_star: time blocks across the GPUs of the box)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import sharding, synth
+    if args.mode == 'test':
+        raise SystemExit("--mode test sweeps the delay block by block and runs on one GPU only")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(cor.device)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", cor.device))
+    rank = dist.get_rank()
+    S = int(cor.num_samp)
+    if args.output is None:                      # every rank must agree on the file name rank 0 writes
+        name = [cor.output_file]
+        dist.broadcast_object_list(name, src=0)
+        cor.output_file = name[0]
+    if args.input0 and args.input1:
+        src0, src1 = args.input0, args.input1
+    else:
+        src0, src1 = synth.tiled_recording_lazy(n_blocks, S, base_blocks=min(8, n_blocks), delay=args.synthetic_delay,
+                                                window_blocks=cor.batch_blocks)
+    t_run = time.perf_counter()
+    rows = sharding.run_recording_sharded(cor, src0, src1, n_blocks)
+    dist.barrier()
+    if rank == 0:
+        print(f'wrote {cor.output_file} ({len(rows)} rows from {world} GPUs); estimated delay {1e6 * cor.calibrated_delay:.6f} us')
+        if args.timing:
+            import json
+            phases["run_s"] = time.perf_counter() - t_run
+            phases["total_s"] = time.perf_counter() - t_start
+            phases["csv_bytes"] = os.path.getsize(cor.output_file)
+            phases["rows"] = len(rows)
+            phases["gpus"] = world
+            print(json.dumps({"effex_b200_cli_timing": phases}))
+    cor.close()
+    dist.destroy_process_group()
     return 0
 
 

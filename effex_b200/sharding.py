@@ -208,3 +208,72 @@ def sharded_lag(engine, d_iq0: torch.Tensor, d_iq1: torch.Tensor, group=None, ds
     if rank != dst:
         return None
     return engine.lag_finish(xacc)
+
+
+def run_recording_sharded(cor, src0, src1, n_blocks: int | None = None, write_csv: bool = True, calibrate: bool = True,
+                          group=None, dst: int = 0):
+    """One spectrum/continuum run of `Correlator` over the ranks of `group` (one process per GPU): the
+    drop-in's run loop (effex.py:326-417: first block pair calibrates and yields no row, every later block
+    pair one row) with the blocks time-sharded by contiguous ranges.  `src0/src1` are two recordings every
+    rank can read -- paths of regular files, or uint8 arrays / `synth.TiledRecording`s.  Rank `dst` calibrates
+    on block 0 and broadcasts the delay, every rank turns its own block range into rows
+    (`fx_process_host`), rank `dst` gathers them in block order and writes the reference's CSV.
+    Returns the rows on `dst` (None elsewhere)."""
+    import os
+    from .ingest import RecordingReader, _is_regular_file
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if cor.mode == 'TEST':
+        raise ValueError("TEST mode sweeps the delay block by block; it does not shard")
+    S, N = int(cor.num_samp), int(cor.nbins)
+    files = _is_regular_file(src0) and _is_regular_file(src1)
+    have = (min(os.path.getsize(src0), os.path.getsize(src1)) if files else min(src0.size, src1.size)) // (2 * S)
+    n_blocks = have if n_blocks is None else min(int(n_blocks), have)
+    dev = torch.device("cuda", cor.device)
+
+    def block(src, b0, nb):
+        if files:
+            return np.fromfile(src, dtype=np.uint8, count=2 * S * nb, offset=2 * S * b0)
+        return src[2 * S * b0:2 * S * (b0 + nb)]
+    first = 0
+    if calibrate and n_blocks > 0:
+        delay = torch.zeros(1, dtype=torch.float64, device=dev)
+        if rank == dst:
+            cor.gpu_iq_0 = torch.from_numpy(np.ascontiguousarray(block(src0, 0, 1))).to(dev)
+            cor.gpu_iq_1 = torch.from_numpy(np.ascontiguousarray(block(src1, 0, 1))).to(dev)
+            cor._calibrate_task()
+            delay[0] = cor.calibrated_delay
+        if world > 1:
+            dist.broadcast(delay, src=dst, group=group)
+        cor.calibrated_delay = float(delay.item())
+        first = 1
+    n_rows = max(n_blocks - first, 0)
+    start, count = shard_range(n_rows, world, rank)
+    eng = cor._main_engine(max_blocks=max(1, min(cor.batch_blocks, max(count, 1))))
+    rows = np.empty((count, N), dtype=np.complex64)
+    if files and count:
+        reader = RecordingReader(src0, src1, S, batch_blocks=cor.batch_blocks, skip_blocks=first + start, max_blocks=count)
+        for raw0, raw1, b0, nb in reader:
+            eng.process_host(raw0, raw1, nb, out=rows[b0:b0 + nb])
+    else:
+        for b0 in range(0, count, cor.batch_blocks):
+            nb = min(cor.batch_blocks, count - b0)
+            eng.process_host(np.ascontiguousarray(block(src0, first + start + b0, nb)),
+                             np.ascontiguousarray(block(src1, first + start + b0, nb)), nb, out=rows[b0:b0 + nb])
+    drows = torch.from_numpy(rows).to(dev)
+    allrows = gather_rows(drows, n_rows, dst=dst, group=group) if world > 1 else drows
+    if rank != dst:
+        return None
+    out = allrows.cpu().numpy()
+    if cor.mode == 'CONTINUUM':
+        out = out.astype(np.complex128).mean(axis=1) / cor.bandwidth
+    if write_csv:
+        cor._write_metadata()
+        writer = cor._start_writer()
+        try:
+            data = out.reshape(-1, 1) if cor.mode == 'CONTINUUM' else out
+            for b0 in range(0, len(data), 256):
+                writer.put(data[b0:b0 + 256])
+        finally:
+            writer.close()
+    return out

@@ -264,3 +264,57 @@ def test_two_gpus_one_process_peer_access():
     np.testing.assert_allclose(acc["flat"].cpu().numpy(), 4 * want.numpy(), rtol=1e-12, atol=1e-9)
     for eng in engs:
         eng.close()
+
+
+def test_sharded_run_loop_on_one_rank_equals_run_recording(tmp_path):
+    """run_recording_sharded without a process group is the drop-in's run loop: calibration on block 0,
+    one row per later block, the reference's CSV"""
+    from effex_b200.correlator import Correlator
+    from effex_b200 import csvio
+    S, N, nb = 2**15, 1024, 9
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=11, seed=21)
+    a = Correlator(num_samp=S, nbins=N, output_file=str(tmp_path / "a.csv"), batch_blocks=4)
+    rows_a = a.run_recording(raw0, raw1)
+    b = Correlator(num_samp=S, nbins=N, output_file=str(tmp_path / "b.csv"), batch_blocks=4)
+    rows_b = sharding.run_recording_sharded(b, raw0, raw1)
+    assert a.calibrated_delay == b.calibrated_delay
+    np.testing.assert_array_equal(rows_a, rows_b)
+    assert open(tmp_path / "a.csv", "rb").read() == open(tmp_path / "b.csv", "rb").read()
+    p0, p1 = tmp_path / "c0.iq", tmp_path / "c1.iq"
+    raw0.tofile(p0); raw1.tofile(p1)
+    c = Correlator(num_samp=S, nbins=N, output_file=str(tmp_path / "c.csv"), batch_blocks=4)
+    rows_c = sharding.run_recording_sharded(c, str(p0), str(p1))
+    np.testing.assert_array_equal(rows_a, rows_c)
+    a.close(); b.close(); c.close()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_torchrun_cli_time_shards_the_run(tmp_path, world):
+    """`torchrun --nproc-per-node N -m effex_b200 ...` writes the CSV of the one-GPU command: same header,
+    same number of rows, rows equal to float32 rounding (the batches differ, so not bit for bit)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import subprocess
+    import sys
+    from effex_b200 import csvio
+    S, N = 2**15, 1024
+    nb = int(np.ceil(1 * 2.4e6 / S))                      # --time 1 (the reference refuses less): 74 blocks
+    raw0, raw1 = synth.tiled_recording(nb, S, base_blocks=8, delay=11, seed=21)
+    p0, p1 = tmp_path / "c0.iq", tmp_path / "c1.iq"
+    raw0.tofile(p0); raw1.tofile(p1)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ["--time", "1", "--num_samp", str(S), "--resolution", str(N), "--omit_plot", "1",
+              "--loglevel", "ERROR", "--input0", str(p0), "--input1", str(p1)]
+    one = subprocess.run([sys.executable, "-m", "effex_b200", *common, "--output", str(tmp_path / "one.csv")],
+                         cwd=root, capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stderr[-1500:]
+    port = 29700 + os.getpid() % 2000 + world
+    many = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "effex_b200", *common,
+                           "--output", str(tmp_path / "many.csv")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert many.returncode == 0, many.stderr[-1500:]
+    m1, r1 = csvio.read_rows(str(tmp_path / "one.csv"))
+    m2, r2 = csvio.read_rows(str(tmp_path / "many.csv"))
+    assert m1 == m2 and r1.shape == r2.shape == (nb - 1, N)
+    np.testing.assert_allclose(r2, r1, rtol=0, atol=2e-6 * np.abs(r1).max())
+    assert open(tmp_path / "one.csv").readlines()[:2] == open(tmp_path / "many.csv").readlines()[:2]
