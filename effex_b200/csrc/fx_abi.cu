@@ -414,6 +414,16 @@ int int_groups() {
     return g;
 }
 
+// nbins = G*4096, reference mode: the persistent TMEM/TMA head kernel (default) or the two-phase one
+// (EFFEX_FX_HEAD2=0, kept for the streaming spans and as an on-device cross-check)
+bool head_persistent() {
+    static const bool on = [] {
+        const char *e = getenv("EFFEX_FX_HEAD2");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 size_t z_budget() {
     if (const char *e = getenv("EFFEX_FX_Z_ELEMS")) {
         const long long v = atoll(e);
@@ -571,6 +581,23 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         const long long nb = std::min(chunk, n_blocks - b0);
         const uint8_t *c0 = d_iq0 + 2 * S * b0, *c1 = d_iq1 + 2 * S * b0;
         const unsigned long long *su = h->d_sums + 4 * b0;
+        h->planning_big = true;
+        rc = plan_segments(h, nb * G, P);                                 // virtual blocks (block, k1) / (block, tile)
+        h->planning_big = false;
+        if (rc) return rc;
+        if (head_persistent()) {
+            // one persistent CTA per SM walks the same segments as the tail kernel, over (block, n2 tile)
+            Head2Params hp;
+            hp.iq0 = c0; hp.iq1 = c1; hp.S = S; hp.P = P; hp.taps = h->d_taps_u8; hp.sums = su;
+            hp.dc_remove = h->cfg.dc_remove; hp.twh = h->d_twH; hp.z = h->d_z;
+            hp.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); hp.cta_first = h->d_plan + h->off_cta;
+            switch (h->logG) {
+                case 1: head2_kernel<1><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                case 2: head2_kernel<2><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                case 3: head2_kernel<3><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                default: head2_kernel<4><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+            }
+        } else {
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((P + kHeadFrames - 1) / kHeadFrames), (unsigned)nb);
         switch (h->logG) {
             case 1: head_kernel<1, false><<<hg, 256, (4096u << 1), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
@@ -578,11 +605,8 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
             case 3: head_kernel<3, false><<<hg, 256, (4096u << 3), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
             default: head_kernel<4, false><<<hg, 256, (4096u << 4), h->stream>>>(c0, c1, S, 0, P, h->d_taps_u8, su, h->cfg.dc_remove, S, nullptr, nullptr, h->d_twH, h->d_z); break;
         }
+        }
         FX_LAUNCH_CHECK(h, "bigfft_head");
-        h->planning_big = true;
-        rc = plan_segments(h, nb * G, P);                                 // virtual blocks (block, k1)
-        h->planning_big = false;
-        if (rc) return rc;
         TailParams prm;
         prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
         prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
@@ -1447,6 +1471,10 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
                                          (int)sizeof(fx::bigfft::SmemT)));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(fx::bigfft::SmemT)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
+        CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
         if (h->big) {    // the intermediate Z of the head/tail pair: at most 1 GiB, or what max_blocks blocks need
             const size_t per_block = (size_t)h->P * cfg->nbins;
             const size_t want = std::min<size_t>(z_budget(), per_block * (size_t)cfg->max_blocks);

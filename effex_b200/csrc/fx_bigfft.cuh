@@ -39,7 +39,13 @@ using fused4096::TILE;
 //      the CTA's slice staged in shared memory), the next batch's raw loads already in flight, and one
 //      16-byte store per k1 into Z (256-byte runs per warp half).
 // grid = (4096/TN2, ceil(P/kHeadFrames), n_blocks), 256 threads, dynamic smem G*4 KB
-constexpr int kHeadFrames = 64;
+#ifndef FX_HEAD_FRAMES
+#define FX_HEAD_FRAMES 64
+#endif
+constexpr int kHeadFrames = FX_HEAD_FRAMES;
+#ifndef FX_HEAD_EARLY
+#define FX_HEAD_EARLY 0
+#endif
 #ifndef FX_HEAD_CTAS
 #define FX_HEAD_CTAS 2
 #endif
@@ -92,7 +98,11 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
     };
     auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i >= 0 at this position
         const long long s = (long long)i * NB;
+#ifdef FX_HEAD_NOLOAD
+        return (uint32_t)(s + n) * 2654435761u;          // timing experiment only: no memory access
+#else
         return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
+#endif
     };
     auto raw_hist = [&](int i) -> uint32_t {       // warm-up only: frames -3..-1 come from the halo (streaming mode)
         if (!SPAN || i >= 0) return raw(i);
@@ -120,15 +130,26 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         }
     }
     for (int ib = i0; ib < i1; ib += G) {
+#if FX_HEAD_EARLY
+        // next batch's bytes: issued before this batch's FIR, in flight during both phases
+        uint32_t wn[G];
+#pragma unroll
+        for (int f = 0; f < G; ++f) wn[f] = ib + G + f < i1 ? raw(ib + G + f) : 0u;
+#endif
 #pragma unroll
         for (int f = 0; f < G; ++f) {
             const C2 o = push(w[f]);
             W[f][t] = make_float4(o.r.x, o.r.y, o.i.x, o.i.y);
         }
         __syncthreads();
+#if FX_HEAD_EARLY
+#pragma unroll
+        for (int f = 0; f < G; ++f) w[f] = wn[f];
+#else
         // next batch's bytes: in flight during phase 2
 #pragma unroll
         for (int f = 0; f < G; ++f) w[f] = ib + G + f < i1 ? raw(ib + G + f) : 0u;
+#endif
         if (ib + fs < i1) {
             C2 v[G];
 #pragma unroll
@@ -151,11 +172,200 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
                     const float2 wk = s_tw[k1][j2];
                     y = cmuls(y, wk.x, wk.y);
                 }
+#ifdef FX_HEAD_NOSTORE
+                if (k1 == 0 || y.r.x == 1.2345e30f)             // timing experiment only: 1/G of the stores
+#endif
                 __stcs(zf + (long long)k1 * N, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
             }
         }
         __syncthreads();
     }
+}
+
+// ---- head, persistent variant ---------------------------------------------------------------------
+// The same arithmetic as head_kernel with the fused kernel's machinery instead of two phases around a
+// shared-memory transpose: a thread owns 16 points of the frame, n = n1*4096 + n2 with n1 = r % G and
+// n2 = tile*(4096/G) + 256*(r / G) + t, so the G-point DFT over n1 runs on its own registers; the FIR state
+// (16 points x 12 floats) and the taps live in TENSOR MEMORY, the raw bytes arrive through a ring of TMA bulk
+// copies (32 rows of 512 bytes per frame) with full/empty mbarriers and no CTA-wide barrier, and every
+// thread stores its 16 values of Z.  One persistent CTA (8 compute warps + 1 producer warp) per SM walks segments of virtual blocks
+// vb = block*G + tile -- the SAME segment plan the tail kernel walks over vb = block*G + k1.
+// Reference mode only (whole blocks, per-block mean, zero history); head_kernel keeps the streaming spans.
+#ifndef FX_HRING
+#define FX_HRING 4
+#endif
+constexpr int HRING = FX_HRING;
+struct __align__(16) SmemH {
+    unsigned short raw[HRING][2][16][256];       // 4 x 16 KB: [slot][channel][point slot r][t] (I, Q) byte pairs
+    unsigned long long full[HRING], empty[HRING];
+    uint32_t tmem_base;
+};
+struct Head2Params {
+    const uint8_t *iq0, *iq1;        // [n_blocks][2*S]
+    long long S;
+    int P;                           // frames per block
+    const float *taps;               // [4][NB] reversed within a branch, scaled by 1/127.5
+    const unsigned long long *sums;  // [n_blocks][2 ch][2 comp]
+    int dc_remove;
+    const float2 *twh;               // W_NB^(n2*k1), [G][4096]
+    float4 *z;                       // [n_blocks][P][G][4096]
+    const Segment *segs;             // segments over virtual blocks vb = block*G + tile
+    const int *cta_first;
+};
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fused4096::smem_u32(bar)) : "memory");
+}
+
+constexpr int kHead2Threads = 288;      // 8 compute warps + the producer warp
+template <int LOGG>
+__global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Params prm) {
+    using namespace fused4096;
+    constexpr int G = 1 << LOGG;
+    constexpr int NB = N << LOGG;                  // nbins
+    constexpr int TW = N >> LOGG;                  // n2 values per tile = 256 * (16 / G)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemH &sm = *reinterpret_cast<SmemH *>(smem_raw);
+    const int t = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+    const int lane = t & 31;
+    if (t == 0) {
+        for (int s = 0; s < HRING; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 8);            // one arrival per warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_pts = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(256 * (warp >> 2));
+
+    const int seg_begin = prm.cta_first[blockIdx.x], seg_end = prm.cta_first[blockIdx.x + 1];
+    // ---- producer warp (warp 8): walks the CTA's ingest items in order, item q -> ring slot q % HRING; lane =
+    //      16*channel + r issues the 512-byte row of point slot r (ptxas serialises the 32 bulk copies of a
+    //      frame on the uniform datapath: ~25 cycles each, which is why they have a warp of their own) ----
+    if (warp == 8) {
+        uint32_t pcnt = 0;
+        const int ch = lane >> 4, r = lane & 15;
+        for (int ps = seg_begin; ps < seg_end; ++ps) {
+            const Segment g = prm.segs[ps];
+            const int g0 = g.f0 > 3 ? g.f0 - 3 : 0;
+            const int n_ing = g.f0 + g.nf - g0;
+            const int blk = g.block >> LOGG, tile = g.block & (G - 1);
+            const uint8_t *src = (ch ? prm.iq1 : prm.iq0) + 2ll * prm.S * blk +
+                                 2ll * ((long long)g0 * NB + (r & (G - 1)) * N + tile * TW + (r >> LOGG) * 256);
+            for (int pj = 0; pj < n_ing; ++pj, ++pcnt, src += 2ll * NB) {
+                const uint32_t slot = pcnt % HRING;
+                if (pcnt >= HRING) mbar_wait(&sm.empty[slot], ((pcnt / HRING) - 1) & 1u);
+                if (lane == 0) mbar_expect_tx(&sm.full[slot], 2u * 16u * 512u);
+                __syncwarp();
+#ifdef FX_HEAD_NOLOAD
+                tma_load_1d(&sm.raw[slot][ch][r][0], prm.iq0 + 512 * lane, 512u, &sm.full[slot]);   // timing experiment only
+#else
+                tma_load_1d(&sm.raw[slot][ch][r][0], src, 512u, &sm.full[slot]);
+#endif
+            }
+        }
+    }
+
+    uint32_t ccnt = 0;
+    for (int seg = seg_begin; seg < seg_end && warp < 8; ++seg) {
+        const Segment sg = prm.segs[seg];
+        const int blk = sg.block >> LOGG, tile = sg.block & (G - 1);
+        float2 nmI, nmQ;
+        if (prm.dc_remove) {
+            const unsigned long long *su = prm.sums + 4ll * blk;
+            const double inv = 1.0 / (double)prm.S;
+            nmI = f2((float)(128.0 - (double)su[0] * inv), (float)(128.0 - (double)su[2] * inv));
+            nmQ = f2((float)(128.0 - (double)su[1] * inv), (float)(128.0 - (double)su[3] * inv));
+        } else {
+            nmI = f2(0.5f, 0.5f);
+            nmQ = f2(0.5f, 0.5f);
+        }
+        // taps of this tile's points and zero FIR state -> tensor memory; twiddles of its outputs -> registers
+        tmem_wait_st();
+        float2 tw[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n2 = tile * TW + (r >> LOGG) * 256 + t;
+            const int n = (r & (G - 1)) * N + n2;
+            tmem_st4(tm_pts + 16 * r, make_float4(prm.taps[n], prm.taps[(long long)NB + n], prm.taps[2ll * NB + n],
+                                                  prm.taps[3ll * NB + n]));
+            tmem_st4(tm_pts + 16 * r + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            tmem_st4(tm_pts + 16 * r + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+            tmem_st4(tm_pts + 16 * r + 12, make_float4(0.f, 0.f, 0.f, 0.f));
+            // register r of its column's DFT output holds k1 = perm_rp(G, r % G)
+            tw[r] = prm.twh[perm_rp(G, r & (G - 1)) * N + n2];
+        }
+        const int g0 = sg.f0 > 3 ? sg.f0 - 3 : 0;
+        const int n_ing = sg.f0 + sg.nf - g0;
+        float4 *zblk = prm.z + ((long long)blk * prm.P * G) * N + tile * TW + t;
+        const float2 mg = f2(-kMagic, -kMagic);
+#pragma unroll 1
+        for (int j = 0; j < n_ing; ++j, ++ccnt) {
+            const uint32_t slot = ccnt % HRING;
+            mbar_wait(&sm.full[slot], (ccnt / HRING) & 1u);
+            uint32_t cur[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                cur[r] = __byte_perm((uint32_t)sm.raw[slot][0][r][t], (uint32_t)sm.raw[slot][1][r][t], 0x5410);   // (I0,Q0,I1,Q1)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[slot]);
+            tmem_wait_st();                        // the previous frame's state stores have landed
+            C2 v[16];
+            {
+                float4 tp[2], z1[2], z2[2], z3[2];
+                tmem_ld8(tm_pts, tp[0], z1[0]);
+                tmem_ld8(tm_pts + 8, z2[0], z3[0]);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int c = r & 1, nx = c ^ 1;
+                    tmem_wait_ld(tp[c], z1[c], z2[c], z3[c]);
+                    if (r + 1 < 16) {
+                        tmem_ld8(tm_pts + 16 * (r + 1), tp[nx], z1[nx]);
+                        tmem_ld8(tm_pts + 16 * (r + 1) + 8, z2[nx], z3[nx]);
+                    }
+                    const uint32_t w = cur[r];
+                    const float2 yr = f2add(f2add(f2(byte_to_magic<0>(w), byte_to_magic<2>(w)), mg), nmI);
+                    const float2 yi = f2add(f2add(f2(byte_to_magic<1>(w), byte_to_magic<3>(w)), mg), nmQ);
+                    v[r] = {f2fmas(yr, tp[c].x, f2(z1[c].x, z1[c].y)), f2fmas(yi, tp[c].x, f2(z1[c].z, z1[c].w))};
+                    const float2 s1r = f2fmas(yr, tp[c].y, f2(z2[c].x, z2[c].y)), s1i = f2fmas(yi, tp[c].y, f2(z2[c].z, z2[c].w));
+                    const float2 s2r = f2fmas(yr, tp[c].z, f2(z3[c].x, z3[c].y)), s2i = f2fmas(yi, tp[c].z, f2(z3[c].z, z3[c].w));
+                    const float2 s3r = f2muls(yr, tp[c].w), s3i = f2muls(yi, tp[c].w);
+                    tmem_st4(tm_pts + 16 * r + 4, make_float4(s1r.x, s1r.y, s1i.x, s1i.y));
+                    tmem_st4(tm_pts + 16 * r + 8, make_float4(s2r.x, s2r.y, s2i.x, s2i.y));
+                    tmem_st4(tm_pts + 16 * r + 12, make_float4(s3r.x, s3r.y, s3i.x, s3i.y));
+                }
+            }
+            if (g0 + j < sg.f0) continue;          // history only
+            if constexpr (G == 16) {
+                dft16(v);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16 / G; ++c) dft_small<G>(&v[c * G]);
+            }
+            float4 *zf = zblk + (long long)(g0 + j) * G * N;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int k1 = perm_rp(G, r & (G - 1));
+                C2 y = v[r];
+                if (k1 != 0) y = cmuls(y, tw[r].x, tw[r].y);
+#ifdef FX_HEAD_NOSTORE
+                if (k1 == 0 || y.r.x == 1.2345e30f)             // timing experiment only: 1/G of the stores
+#endif
+#ifdef FX_Z_ST_DEFAULT
+                zf[(long long)k1 * N + (r >> LOGG) * 256] = make_float4(y.r.x, y.r.y, y.i.x, y.i.y);
+#else
+                __stcs(zf + (long long)k1 * N + (r >> LOGG) * 256, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
+#endif
+            }
+        }
+    }
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(sm.tmem_base, 512);
 }
 
 // ---- tail ------------------------------------------------------------------------------------------
