@@ -986,6 +986,12 @@ int lag_tn2() {
     return v;
 }
 
+// lag head: the register/one-exchange kernel (default) or the shared-memory Stockham one (EFFEX_FX_LAG_HEAD2=0)
+bool lag_head_registers() {
+    static bool v = [] { const char *e = getenv("EFFEX_FX_LAG_HEAD2"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
 bool lag_force_generic() {
     static bool v = [] { const char *e = getenv("EFFEX_FX_LAG_GENERIC"); return e && atoi(e) != 0; }();
     return v;
@@ -1027,6 +1033,13 @@ int ensure_lag(fx_handle *h, long long M) {
         FX_CUDA(h, cudaMemcpy(h->d_lag_twAp, twAp.data(), twAp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         FX_CUDA(h, cudaMemcpy(h->d_lag_twBp, twBp.data(), twBp.size() * sizeof(float4), cudaMemcpyHostToDevice));
         const int head_smem = 2 * 4096 * (int)sizeof(float4) + 256 * (int)sizeof(float2);
+#define FX_LAG_ATTR(LG)                                                                                                     \
+    FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head2_kernel<true, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    (int)fx::lag::LagSplit<LG>::smem));                                                      \
+    FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head2_kernel<false, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)fx::lag::LagSplit<LG>::smem))
+        FX_LAG_ATTR(5); FX_LAG_ATTR(6); FX_LAG_ATTR(7); FX_LAG_ATTR(8);
+#undef FX_LAG_ATTR
         FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
         FX_CUDA(h, cudaFuncSetAttribute(fx::lag::lag_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
         FX_CUDA(h, cudaFuncSetAttribute(fx::bigfft::tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1063,10 +1076,29 @@ int lag_head_tail(fx_handle *h, const void *d0, const void *d1, long long n_in, 
     const size_t smem = 2 * (size_t)G * tn2 * sizeof(float4) + (size_t)G * sizeof(float2);
     for (long long r0 = 0; r0 < nb; r0 += 65535) {
         const long long nr = std::min<long long>(65535, nb - r0);
-        dim3 grid(fx::fused4096::N / tn2, (unsigned)nr);
-        fx::lag::lag_head_kernel<U8><<<grid, 256, smem, h->stream>>>(d0, d1, n_in, logG, tn2, block0 + r0, h->d_sums,
-                                                                    h->cfg.dc_remove, conj_in, h->d_lag_twH,
-                                                                    h->d_lag_z + (size_t)r0 * G * fx::fused4096::N);
+        float4 *zdst = h->d_lag_z + (size_t)r0 * G * fx::fused4096::N;
+        if (lag_head_registers()) {
+            // the G-point transform in registers around one shared-memory exchange
+#define FX_LAG_HEAD2(LG)                                                                                          \
+    fx::lag::lag_head2_kernel<U8, LG><<<dim3(fx::fused4096::N / fx::lag::LagSplit<LG>::TN2, (unsigned)nr), fx::lag::kLagThreads,   \
+                                        fx::lag::LagSplit<LG>::smem, h->stream>>>(                                \
+        d0, d1, n_in, block0 + r0, h->d_sums, h->cfg.dc_remove, conj_in, h->d_lag_twH, zdst)
+            switch (logG) {
+                case 1: FX_LAG_HEAD2(1); break;
+                case 2: FX_LAG_HEAD2(2); break;
+                case 3: FX_LAG_HEAD2(3); break;
+                case 4: FX_LAG_HEAD2(4); break;
+                case 5: FX_LAG_HEAD2(5); break;
+                case 6: FX_LAG_HEAD2(6); break;
+                case 7: FX_LAG_HEAD2(7); break;
+                default: FX_LAG_HEAD2(8); break;
+            }
+#undef FX_LAG_HEAD2
+        } else {
+            dim3 grid(fx::fused4096::N / tn2, (unsigned)nr);
+            fx::lag::lag_head_kernel<U8><<<grid, 256, smem, h->stream>>>(d0, d1, n_in, logG, tn2, block0 + r0, h->d_sums,
+                                                                        h->cfg.dc_remove, conj_in, h->d_lag_twH, zdst);
+        }
         FX_LAUNCH_CHECK(h, "lag_head");
     }
     h->planning_big = true;

@@ -172,6 +172,140 @@ __global__ void __launch_bounds__(256) lag_head_kernel(const void *__restrict__ 
     }
 }
 
+// ---- the same head with the G-point transform in REGISTERS ----------------------------------------------
+// lag_head_kernel walks log4(G) Stockham passes through shared memory (10 x 16 bytes of LSU traffic per
+// element: 207 us of shared-memory time for C2's 92 blocks, the kernel took 460 us).  Here G = Ga*Gb
+// (Ga = min(G, 16)), n1 = Gb*a + b, k1 = ka + Ga*kb:
+//     W_G^(n1*k1) = W_Ga^(a*ka) * W_G^(b*ka) * W_Gb^(b*kb)
+//   step 1  thread (b, n2): its Ga inputs x[(Gb*a + b)*4096 + n2] (rows past the data are the zero padding and
+//           are never read), DFT over a in registers with the packed-FP32 butterflies of fx_common.cuh,
+//           twiddle W_G^(b*ka)                                   -> shared memory [ka][b][n2]   (one exchange)
+//   step 2  thread (ka, n2): DFT over b in registers, twiddle W_M^(n2*k1), one 16-byte store per k1 into Z
+// (G <= 16: no exchange at all).  grid = (4096/TN2, blocks), 256 threads, TN2 = 256/Gb columns per CTA,
+// shared memory G*TN2*16 B (64 KB for G >= 32) + the W_G table.
+#ifndef FX_LAG_THREADS
+#define FX_LAG_THREADS 256
+#endif
+// three CTAs per SM (80 registers, no spills; the 64 KB exchange tiles allow no more): the kernel is
+// latency-bound, 458 -> 400 us for C2's 92 blocks against two per SM (profiles/r02_lag_head2.txt)
+#ifndef FX_LAG_MINB
+#define FX_LAG_MINB 3
+#endif
+constexpr int kLagThreads = FX_LAG_THREADS;
+template <int LOGG>
+struct LagSplit {
+    static constexpr int G = 1 << LOGG;
+    static constexpr int LA = LOGG < 4 ? LOGG : 4;
+    static constexpr int Ga = 1 << LA, Gb = G / Ga;
+    static constexpr int TN2 = kLagThreads / Gb;
+    static constexpr size_t smem = (Gb > 1 ? (size_t)G * TN2 * sizeof(float4) : 0) + (size_t)G * sizeof(float2);
+};
+template <int R>
+__device__ __forceinline__ void dft_regs(C2 *v) {
+    if constexpr (R == 16) {
+        C2(&v16)[16] = reinterpret_cast<C2(&)[16]>(*v);
+        dft16(v16);
+    } else if constexpr (R > 1) {
+        fused4096::dft_small<R>(v);
+    }
+}
+template <bool U8, int LOGG>
+__global__ void __launch_bounds__(kLagThreads, FX_LAG_MINB) lag_head2_kernel(const void *__restrict__ in0, const void *__restrict__ in1,
+                                                           long long n, long long block0,
+                                                           const unsigned long long *__restrict__ sums, int dc_remove,
+                                                           int conj_in, const float2 *__restrict__ twh,
+                                                           float4 *__restrict__ z) {
+    using L = LagSplit<LOGG>;
+    constexpr int G = L::G, Ga = L::Ga, Gb = L::Gb, TN2 = L::TN2;
+    extern __shared__ __align__(16) unsigned char lag_smem[];
+    float4 *X = reinterpret_cast<float4 *>(lag_smem);                                   // [Ga][Gb][TN2]
+    float2 *tw = reinterpret_cast<float2 *>(lag_smem + (Gb > 1 ? (size_t)G * TN2 * sizeof(float4) : 0));   // W_G^i
+    const int t = threadIdx.x;
+    const long long blk = block0 + blockIdx.y;
+    const int n2_0 = blockIdx.x * TN2;
+    for (int i = t; i < G; i += kLagThreads) {
+        float sn, cs;
+        sincospif(-2.f * (float)i / (float)G, &sn, &cs);
+        tw[i] = make_float2(cs, sn);
+    }
+    float m0i = 127.5f, m0q = 127.5f, m1i = 127.5f, m1q = 127.5f;
+    if (U8 && dc_remove) {
+        const double inv = 1.0 / (double)n;
+        m0i = (float)((double)sums[4 * blk + 0] * inv); m0q = (float)((double)sums[4 * blk + 1] * inv);
+        m1i = (float)((double)sums[4 * blk + 2] * inv); m1q = (float)((double)sums[4 * blk + 3] * inv);
+    }
+    const float sc = 1.0f / 127.5f;
+    const float cj = conj_in ? -1.f : 1.f;
+    if (Gb > 1) __syncthreads();                       // the W_G table is read in step 1
+    float4 *zb = z + (long long)blockIdx.y * G * fused4096::N;
+    // ---- step 1 ----
+    {
+        const int b = t / TN2, j2 = t % TN2, n2 = n2_0 + j2;
+        C2 v[Ga];
+#pragma unroll
+        for (int a = 0; a < Ga; ++a) {
+            const long long s = (long long)(Gb * a + b) * fused4096::N + n2;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < n) {
+                if (U8) {
+                    const uchar2 pa = reinterpret_cast<const uchar2 *>(in0)[blk * n + s];
+                    const uchar2 pb = reinterpret_cast<const uchar2 *>(in1)[blk * n + s];
+                    q = make_float4(((float)pa.x - m0i) * sc, ((float)pb.x - m1i) * sc, ((float)pa.y - m0q) * sc * cj,
+                                    ((float)pb.y - m1q) * sc * cj);
+                } else {
+                    const float2 pa = reinterpret_cast<const float2 *>(in0)[blk * n + s];
+                    const float2 pb = in1 ? reinterpret_cast<const float2 *>(in1)[blk * n + s] : make_float2(0.f, 0.f);
+                    q = make_float4(pa.x, pb.x, pa.y * cj, pb.y * cj);
+                }
+            }
+            v[a] = {f2(q.x, q.y), f2(q.z, q.w)};
+        }
+        dft_regs<Ga>(v);
+#pragma unroll
+        for (int j = 0; j < Ga; ++j) {
+            const int ka = fused4096::perm_rp(Ga, j);
+            C2 y = v[j];
+            if (Gb > 1) {
+                if (ka != 0) {                          // b == 0 multiplies by 1 (kept: no divergence inside a warp for TN2 >= 32)
+                    const float2 w = tw[(b * ka) & (G - 1)];
+                    y = cmuls(y, w.x, w.y);
+                }
+                X[(ka * Gb + b) * TN2 + j2] = make_float4(y.r.x, y.r.y, y.i.x, y.i.y);
+            } else {
+                if (ka != 0) {
+                    const float2 w = twh[(long long)ka * fused4096::N + n2];
+                    y = cmuls(y, w.x, w.y);
+                }
+                __stcs(zb + (long long)ka * fused4096::N + n2, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
+            }
+        }
+    }
+    if (Gb == 1) return;
+    __syncthreads();
+    // ---- step 2 ----
+#pragma unroll 1
+    for (int task = t; task < Ga * TN2; task += kLagThreads) {
+        const int ka = task / TN2, j2 = task % TN2, n2 = n2_0 + j2;
+        C2 u[Gb];
+#pragma unroll
+        for (int b = 0; b < Gb; ++b) {
+            const float4 q = X[(ka * Gb + b) * TN2 + j2];
+            u[b] = {f2(q.x, q.y), f2(q.z, q.w)};
+        }
+        dft_regs<Gb>(u);
+#pragma unroll
+        for (int j = 0; j < Gb; ++j) {
+            const int k1 = ka + Ga * fused4096::perm_rp(Gb, j);
+            C2 y = u[j];
+            if (k1 != 0) {
+                const float2 w = twh[(long long)k1 * fused4096::N + n2];
+                y = cmuls(y, w.x, w.y);
+            }
+            __stcs(zb + (long long)k1 * fused4096::N + n2, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
+        }
+    }
+}
+
 // d_xacc[k1 + G*k2] (=|+=) sum over the segments of virtual block k1 of part_x[s][k2].   grid = (M/256)
 __global__ void __launch_bounds__(256) lag_fold_kernel(const float2 *__restrict__ part_x, int logG,
                                                        const int *__restrict__ vblk_first, int first,
