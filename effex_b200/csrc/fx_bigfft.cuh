@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
     if (t == 0) {
         for (int s = 0; s < HRING; ++s) {
             mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], 8);            // one arrival per warp
+            mbar_init(&sm.empty[s], 256);          // every compute thread arrives once it has read its bytes
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -310,8 +310,7 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
 #pragma unroll
             for (int r = 0; r < 16; ++r)
                 cur[r] = __byte_perm((uint32_t)sm.raw[slot][0][r][t], (uint32_t)sm.raw[slot][1][r][t], 0x5410);   // (I0,Q0,I1,Q1)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[slot]);
+            mbar_arrive(&sm.empty[slot]);          // (per thread, not per warp: compute-sanitizer's racecheck follows it)
             tmem_wait_st();                        // the previous frame's state stores have landed
             C2 v[16];
             {
