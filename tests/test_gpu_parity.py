@@ -435,3 +435,48 @@ def test_no_dc_removal_generic_and_fused_agree_with_oracle():
         ref = orc.pfb_xcorr(orc.unpack_iq(raw0), orc.unpack_iq(raw1), 4, N, w, 2.4e6, 1.4204e9, 0.0)
         assert_close(x, ref, what=f"no DC removal N={N}")
         eng.close()
+
+
+# --------------------------------------------------------------------------
+# the previous-generation kernels kept behind environment switches (read once per process, hence a subprocess):
+# the two-phase head_kernel in reference mode (EFFEX_FX_HEAD2=0) and the shared-memory Stockham lag head
+# (EFFEX_FX_LAG_HEAD2=0) must keep giving the persistent / register kernels' results
+# --------------------------------------------------------------------------
+_FALLBACK_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from effex_b200 import synth
+from effex_b200.engine import FxEngine
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+out = {}
+for N, P, nb in ((8192, 5, 3), (65536, 4, 2)):
+    S = P * N
+    raw0, raw1 = synth.correlated_pair(nb * S, delay=3, dc0=0.013 - 0.02j, seed=N)
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    out["x%%d" %% N] = eng.process(dev(raw0), dev(raw1), nb).cpu().numpy()
+    eng.close()
+n, nblk = 2**16, 2
+raw0, raw1 = synth.correlated_pair(nblk * n, delay=-7, seed=9)
+eng = FxEngine(n, 8, 1, max_blocks=nblk)
+r = eng.lag(dev(raw0), dev(raw1), nblk)
+out["lag"] = np.array([r[0], r[1]] + list(r[2:5]), dtype=np.float64)
+eng.close()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_fallback_kernels_behind_env_switches(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("new", {}), ("old", {"EFFEX_FX_HEAD2": "0", "EFFEX_FX_LAG_HEAD2": "0"})):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", _FALLBACK_CHILD % root, path], env=dict(os.environ, **env), check=True,
+                       timeout=600)
+        res[tag] = np.load(path)
+    for k in ("x8192", "x65536"):
+        assert np.abs(res["new"][k] - res["old"][k]).max() <= 2e-6 * np.abs(res["old"][k]).max(), k
+    assert res["new"]["lag"][0] - res["new"]["lag"][1] == -7
+    np.testing.assert_array_equal(res["new"]["lag"][:2], res["old"]["lag"][:2])
+    np.testing.assert_allclose(res["new"]["lag"][2:], res["old"]["lag"][2:], rtol=1e-5)
