@@ -38,6 +38,7 @@ struct fx_handle {
     bool big = false;          // nbins = 2^logG * 4096, ntaps = 4: head + tail kernels (fx_bigfft.cuh)
     int logG = 0;
     uint8_t *d_halo_pad[2] = {nullptr, nullptr};   // fused path: the caller's halo, right-aligned in whole super-frames
+    uint8_t *d_halo_big[2] = {nullptr, nullptr};   // big path: an aligned copy of the caller's 3 halo frames
     float2 *d_twH = nullptr;   // big path: W_nbins^(n2*k1), [G][4096]
     float4 *d_z = nullptr;     // big path: Z[blocks of a chunk][P][G][4096]
     size_t z_cap = 0;          // in float4 elements
@@ -585,11 +586,14 @@ int run_big(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long 
         rc = plan_segments(h, nb * G, P);                                 // virtual blocks (block, k1) / (block, tile)
         h->planning_big = false;
         if (rc) return rc;
-        if (head_persistent()) {
+        // the persistent kernel's TMA bulk copies need 16-byte aligned runs: aligned pointers, num_samp % 8 == 0
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(c1)) & 15) == 0 && (S % 8) == 0;
+        if (head_persistent() && tma_ok) {
             // one persistent CTA per SM walks the same segments as the tail kernel, over (block, n2 tile)
             Head2Params hp;
             hp.iq0 = c0; hp.iq1 = c1; hp.S = S; hp.P = P; hp.taps = h->d_taps_u8; hp.sums = su;
             hp.dc_remove = h->cfg.dc_remove; hp.twh = h->d_twH; hp.z = h->d_z;
+            hp.i_begin = 0; hp.first_hist = 0; hp.mean_count = S; hp.halo0 = hp.halo1 = nullptr;
             hp.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); hp.cta_first = h->d_plan + h->off_cta;
             switch (h->logG) {
                 case 1: head2_kernel<1><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
@@ -655,8 +659,35 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
         FX_CUDA(h, cudaMalloc(&h->d_z, need * sizeof(float4)));
         h->z_cap = need;
     }
+    // the persistent kernel's TMA bulk copies need 16-byte aligned runs; the halo goes through an aligned copy
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(d_iq0) | reinterpret_cast<uintptr_t>(d_iq1)) & 15) == 0 &&
+                        h->d_halo_big[0] != nullptr;
+    const bool persistent = head_persistent() && tma_ok;
+    if (persistent && o.halo0) {
+        const size_t halo_bytes = 3 * (size_t)NB * 2;
+        FX_CUDA(h, cudaMemcpyAsync(h->d_halo_big[0], o.halo0, halo_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        FX_CUDA(h, cudaMemcpyAsync(h->d_halo_big[1], o.halo1, halo_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
     for (long long ib = 0; ib < P; ib += fc) {
         const int n = (int)std::min<long long>(fc, P - ib);
+        h->planning_big = true;
+        rc = plan_segments(h, G, n);                                      // virtual blocks (0, k1) / (0, tile), n frames each
+        h->planning_big = false;
+        if (rc) return rc;
+        if (persistent) {
+            Head2Params hp;
+            hp.iq0 = d_iq0; hp.iq1 = d_iq1; hp.S = o.S; hp.P = n; hp.taps = h->d_taps_u8; hp.sums = h->d_sums;
+            hp.dc_remove = h->cfg.dc_remove; hp.twh = h->d_twH; hp.z = h->d_z;
+            hp.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); hp.cta_first = h->d_plan + h->off_cta;
+            hp.i_begin = (int)ib; hp.first_hist = o.halo0 ? -3 : 0; hp.mean_count = mean_count;
+            hp.halo0 = h->d_halo_big[0]; hp.halo1 = h->d_halo_big[1];
+            switch (h->logG) {
+                case 1: head2_kernel<1><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                case 2: head2_kernel<2><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                case 3: head2_kernel<3><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+                default: head2_kernel<4><<<h->plan_grid, kHead2Threads, sizeof(SmemH), h->stream>>>(hp); break;
+            }
+        } else {
         dim3 hg(fx::fused4096::N / (256 >> h->logG), (unsigned)((n + kHeadFrames - 1) / kHeadFrames), 1);
 #define FX_HEAD_ARGS d_iq0, d_iq1, o.S, (int)ib, (int)ib + n, h->d_taps_u8, h->d_sums, h->cfg.dc_remove, mean_count, o.halo0, o.halo1, h->d_twH, h->d_z
         switch (h->logG) {
@@ -666,11 +697,8 @@ int run_big_span(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, const
             default: head_kernel<4, true><<<hg, 256, (4096u << 4), h->stream>>>(FX_HEAD_ARGS); break;
         }
 #undef FX_HEAD_ARGS
+        }
         FX_LAUNCH_CHECK(h, "bigfft_head");
-        h->planning_big = true;
-        rc = plan_segments(h, G, n);                                      // virtual blocks (0, k1), n frames each
-        h->planning_big = false;
-        if (rc) return rc;
         TailParams prm;
         prm.z = h->d_z; prm.twAp = h->d_twAp; prm.twBp = h->d_twBp;
         prm.segs = reinterpret_cast<const fx::fused4096::Segment *>(h->d_plan); prm.cta_first = h->d_plan + h->off_cta;
@@ -1508,6 +1536,7 @@ int fx_create(const fx_config *cfg, fx_handle **out) {
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
         CREATE_CUDA(cudaFuncSetAttribute(fx::bigfft::head2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fx::bigfft::SmemH)));
         if (h->big) {    // the intermediate Z of the head/tail pair: at most 1 GiB, or what max_blocks blocks need
+            for (int c = 0; c < 2; ++c) CREATE_CUDA(cudaMalloc(&h->d_halo_big[c], 3 * (size_t)cfg->nbins * 2));
             const size_t per_block = (size_t)h->P * cfg->nbins;
             const size_t want = std::min<size_t>(z_budget(), per_block * (size_t)cfg->max_blocks);
             CREATE_CUDA(cudaMalloc(&h->d_z, std::max<size_t>(want, (size_t)fx::bigfft::kHeadFrames * cfg->nbins) * sizeof(float4)));
@@ -1529,7 +1558,7 @@ int fx_destroy(fx_handle *h) {
     if (h->stream_aux) cudaStreamSynchronize(h->stream_aux);
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
-                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_bs_chirp, h->d_bs_B, h->d_bs_a, h->d_bs_tmp, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
+                    h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_bs_chirp, h->d_bs_B, h->d_bs_a, h->d_bs_tmp, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_halo_big[0], h->d_halo_big[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
                     h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};

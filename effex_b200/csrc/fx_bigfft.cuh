@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
 // copies (32 rows of 512 bytes per frame) with full/empty mbarriers and no CTA-wide barrier, and every
 // thread stores its 16 values of Z.  One persistent CTA (8 compute warps + 1 producer warp) per SM walks segments of virtual blocks
 // vb = block*G + tile -- the SAME segment plan the tail kernel walks over vb = block*G + k1.
-// Reference mode only (whole blocks, per-block mean, zero history); head_kernel keeps the streaming spans.
+// Reference mode (whole blocks, per-block mean, zero history) and streaming spans (chunks of one span's frames,
+// recording-wide mean, halo frames); head_kernel remains for inputs that are not 16-byte aligned.
 #ifndef FX_HRING
 #define FX_HRING 4
 #endif
@@ -211,6 +212,12 @@ struct Head2Params {
     float4 *z;                       // [n_blocks][P][G][4096]
     const Segment *segs;             // segments over virtual blocks vb = block*G + tile
     const int *cta_first;
+    // streaming spans (one unit walked in chunks of frames): Z row 0 is frame i_begin of the span, the mean is taken
+    // over mean_count samples, and the frames before frame 0 come from the halo (3 frames of NB samples per channel,
+    // 16-byte aligned) when there is one.  Reference mode: i_begin = 0, first_hist = 0, mean_count = S, no halo.
+    int i_begin, first_hist;
+    long long mean_count;
+    const uint8_t *halo0, *halo1;
 };
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fused4096::smem_u32(bar)) : "memory");
@@ -250,12 +257,16 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
         const int ch = lane >> 4, r = lane & 15;
         for (int ps = seg_begin; ps < seg_end; ++ps) {
             const Segment g = prm.segs[ps];
-            const int g0 = g.f0 > 3 ? g.f0 - 3 : 0;
+            const int lo_f = prm.first_hist - prm.i_begin;             // earliest frame that exists, chunk-relative
+            const int g0 = g.f0 - 3 > lo_f ? g.f0 - 3 : lo_f;
             const int n_ing = g.f0 + g.nf - g0;
             const int blk = g.block >> LOGG, tile = g.block & (G - 1);
-            const uint8_t *src = (ch ? prm.iq1 : prm.iq0) + 2ll * prm.S * blk +
-                                 2ll * ((long long)g0 * NB + (r & (G - 1)) * N + tile * TW + (r >> LOGG) * 256);
-            for (int pj = 0; pj < n_ing; ++pj, ++pcnt, src += 2ll * NB) {
+            const long long row = (long long)(r & (G - 1)) * N + tile * TW + (r >> LOGG) * 256;     // samples into a frame
+            const uint8_t *body = (ch ? prm.iq1 : prm.iq0) + 2ll * prm.S * blk + 2ll * row;
+            const uint8_t *halo = (ch ? prm.halo1 : prm.halo0) + 2ll * row;
+            for (int pj = 0; pj < n_ing; ++pj, ++pcnt) {
+                const long long a = (long long)prm.i_begin + g0 + pj;  // frame of the span (negative: halo)
+                const uint8_t *src = a >= 0 ? body + 2ll * a * NB : halo + 2ll * (a + 3) * NB;
                 const uint32_t slot = pcnt % HRING;
                 if (pcnt >= HRING) mbar_wait(&sm.empty[slot], ((pcnt / HRING) - 1) & 1u);
                 if (lane == 0) mbar_expect_tx(&sm.full[slot], 2u * 16u * 512u);
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
         float2 nmI, nmQ;
         if (prm.dc_remove) {
             const unsigned long long *su = prm.sums + 4ll * blk;
-            const double inv = 1.0 / (double)prm.S;
+            const double inv = 1.0 / (double)prm.mean_count;
             nmI = f2((float)(128.0 - (double)su[0] * inv), (float)(128.0 - (double)su[2] * inv));
             nmQ = f2((float)(128.0 - (double)su[1] * inv), (float)(128.0 - (double)su[3] * inv));
         } else {
@@ -298,7 +309,8 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
             // register r of its column's DFT output holds k1 = perm_rp(G, r % G)
             tw[r] = prm.twh[perm_rp(G, r & (G - 1)) * N + n2];
         }
-        const int g0 = sg.f0 > 3 ? sg.f0 - 3 : 0;
+        const int lo_f = prm.first_hist - prm.i_begin;
+        const int g0 = sg.f0 - 3 > lo_f ? sg.f0 - 3 : lo_f;
         const int n_ing = sg.f0 + sg.nf - g0;
         float4 *zblk = prm.z + ((long long)blk * prm.P * G) * N + tile * TW + t;
         const float2 mg = f2(-kMagic, -kMagic);

@@ -480,3 +480,21 @@ def test_fallback_kernels_behind_env_switches(tmp_path):
     assert res["new"]["lag"][0] - res["new"]["lag"][1] == -7
     np.testing.assert_array_equal(res["new"]["lag"][:2], res["old"]["lag"][:2])
     np.testing.assert_allclose(res["new"]["lag"][2:], res["old"]["lag"][2:], rtol=1e-5)
+
+
+def test_big_nbins_unaligned_input_and_ragged_num_samp():
+    """The persistent head kernel reads through 16-byte TMA bulk copies; inputs that are not 16-byte aligned, or a
+    num_samp that is not a multiple of 8, must take the two-phase kernel and give the same rows."""
+    N, nb = 8192, 3
+    for S, shift in ((4 * N, 2), (4 * N + 6, 0)):
+        raw0, raw1 = synth.correlated_pair(nb * S, delay=3, dc0=0.013 - 0.02j, seed=21)
+        pad0, pad1 = torch.zeros(2 * nb * S + 64, dtype=torch.uint8, device="cuda"), torch.zeros(2 * nb * S + 64, dtype=torch.uint8, device="cuda")
+        d0, d1 = pad0[shift:shift + 2 * nb * S], pad1[shift:shift + 2 * nb * S]
+        d0.copy_(dev(raw0)); d1.copy_(dev(raw1))
+        assert shift == 0 or d0.data_ptr() % 16 != 0
+        eng = FxEngine(S, N, 4, max_blocks=nb)
+        x = eng.process(d0, d1, nb).cpu().numpy()
+        ref = orc.process_recording_u8(raw0, raw1, S, N, 2.4e6, 1.4204e9, 0.0, 4, 0, nb)
+        for b in range(nb):
+            assert_close(x[b], ref[b], what=f"S={S} shift={shift} block {b} vs oracle")
+        eng.close()

@@ -3,7 +3,7 @@
 second path:
   - bigfft::head2_kernel (persistent, tensor-memory FIR state, TMA ring with full/empty mbarriers, producer warp)
     + tail_kernel at 8192 / 16384 / 65536 bins, blocks shorter and longer than the 3 warm-up frames, several
-    segments per CTA;
+    segments per CTA; a streaming span walked in chunks of Z with a halo and recording-wide sums;
   - lag::lag_head2_kernel with and without the shared-memory exchange (G = 2, 4, 32, 64), raw bytes and complex
     input, against the unfused passes."""
 import os, sys
@@ -30,6 +30,27 @@ for N, P, nb in ((8192, 5, 3), (16384, 2, 2), (65536, 6, 2)):
     assert close(x, ref), N
     eng.close()
     print(f"head2 + tail ok N={N}")
+
+# streaming span at 8192 bins walked in chunks of Z, second half with its halo and the recording-wide sums
+os.environ["EFFEX_FX_Z_ELEMS"] = str(16 * 8192)
+S, N, nb = 10 * 8192, 8192, 4
+raw0, raw1 = synth.correlated_pair(nb * S, delay=7, dc0=0.02 + 0.01j, seed=23)
+d0, d1 = dev(raw0), dev(raw1)
+eng = FxEngine(S, N, 4, max_blocks=nb)
+w = orc.pfb_window(4, N)
+f0, f1 = (orc.spectrometer_poly(orc.block_from_u8(r), 4, N, w) for r in (raw0, raw1))
+ref = np.fft.fftshift((f0 * np.conj(f1)).mean(axis=0))
+sums = eng.span_sums(d0, d1, nb)
+tot = eng.new_accumulators()
+half, hb = nb // 2, 2 * 3 * N
+lo = 2 * S * half
+eng.integrate_stream(d0[:lo], d1[:lo], tot, half, sums=sums, total_samp=nb * S)
+eng.integrate_stream(d0[lo:], d1[lo:], tot, nb - half, halo0=d0[lo - hb:lo], halo1=d1[lo - hb:lo], sums=sums, total_samp=nb * S)
+xt, _, _ = FxEngine.finish_integration(tot)
+assert close(xt, ref)
+eng.close()
+del os.environ["EFFEX_FX_Z_ELEMS"]
+print("head2 streaming span ok")
 
 for n, nblk in ((4096, 2), (8192, 3), (2**16, 2), (2**17 - 8, 1)):
     raw0, raw1 = synth.correlated_pair(nblk * n, delay=-7, seed=9)
