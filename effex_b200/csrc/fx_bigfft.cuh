@@ -43,9 +43,6 @@ using fused4096::TILE;
 #define FX_HEAD_FRAMES 64
 #endif
 constexpr int kHeadFrames = FX_HEAD_FRAMES;
-#ifndef FX_HEAD_EARLY
-#define FX_HEAD_EARLY 0
-#endif
 #ifndef FX_HEAD_CTAS
 #define FX_HEAD_CTAS 2
 #endif
@@ -98,11 +95,7 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
     };
     auto raw = [&](int i) -> uint32_t {            // (I0, Q0, I1, Q1) of frame i >= 0 at this position
         const long long s = (long long)i * NB;
-#ifdef FX_HEAD_NOLOAD
-        return (uint32_t)(s + n) * 2654435761u;          // timing experiment only: no memory access
-#else
         return (uint32_t)x0[s] | ((uint32_t)x1[s] << 16);
-#endif
     };
     auto raw_hist = [&](int i) -> uint32_t {       // warm-up only: frames -3..-1 come from the halo (streaming mode)
         if (!SPAN || i >= 0) return raw(i);
@@ -130,26 +123,15 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
         }
     }
     for (int ib = i0; ib < i1; ib += G) {
-#if FX_HEAD_EARLY
-        // next batch's bytes: issued before this batch's FIR, in flight during both phases
-        uint32_t wn[G];
-#pragma unroll
-        for (int f = 0; f < G; ++f) wn[f] = ib + G + f < i1 ? raw(ib + G + f) : 0u;
-#endif
 #pragma unroll
         for (int f = 0; f < G; ++f) {
             const C2 o = push(w[f]);
             W[f][t] = make_float4(o.r.x, o.r.y, o.i.x, o.i.y);
         }
         __syncthreads();
-#if FX_HEAD_EARLY
-#pragma unroll
-        for (int f = 0; f < G; ++f) w[f] = wn[f];
-#else
         // next batch's bytes: in flight during phase 2
 #pragma unroll
         for (int f = 0; f < G; ++f) w[f] = ib + G + f < i1 ? raw(ib + G + f) : 0u;
-#endif
         if (ib + fs < i1) {
             C2 v[G];
 #pragma unroll
@@ -172,9 +154,6 @@ __global__ void __launch_bounds__(256, FX_HEAD_CTAS) head_kernel(const uint8_t *
                     const float2 wk = s_tw[k1][j2];
                     y = cmuls(y, wk.x, wk.y);
                 }
-#ifdef FX_HEAD_NOSTORE
-                if (k1 == 0 || y.r.x == 1.2345e30f)             // timing experiment only: 1/G of the stores
-#endif
                 __stcs(zf + (long long)k1 * N, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
             }
         }
@@ -271,11 +250,7 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
                 if (pcnt >= HRING) mbar_wait(&sm.empty[slot], ((pcnt / HRING) - 1) & 1u);
                 if (lane == 0) mbar_expect_tx(&sm.full[slot], 2u * 16u * 512u);
                 __syncwarp();
-#ifdef FX_HEAD_NOLOAD
-                tma_load_1d(&sm.raw[slot][ch][r][0], prm.iq0 + 512 * lane, 512u, &sm.full[slot]);   // timing experiment only
-#else
                 tma_load_1d(&sm.raw[slot][ch][r][0], src, 512u, &sm.full[slot]);
-#endif
             }
         }
     }
@@ -362,14 +337,7 @@ __global__ void __launch_bounds__(kHead2Threads, 1) head2_kernel(const Head2Para
                 const int k1 = perm_rp(G, r & (G - 1));
                 C2 y = v[r];
                 if (k1 != 0) y = cmuls(y, tw[r].x, tw[r].y);
-#ifdef FX_HEAD_NOSTORE
-                if (k1 == 0 || y.r.x == 1.2345e30f)             // timing experiment only: 1/G of the stores
-#endif
-#ifdef FX_Z_ST_DEFAULT
-                zf[(long long)k1 * N + (r >> LOGG) * 256] = make_float4(y.r.x, y.r.y, y.i.x, y.i.y);
-#else
                 __stcs(zf + (long long)k1 * N + (r >> LOGG) * 256, make_float4(y.r.x, y.r.y, y.i.x, y.i.y));
-#endif
             }
         }
     }
