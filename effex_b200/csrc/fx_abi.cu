@@ -992,10 +992,18 @@ int process_device(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, lon
         return FX_OK;
     }
     if (!d_xspec) return FX_OK;
-    dim3 grid((N + 255) / 256, 1);
+    // two bins per thread when the rows allow 16-byte accesses
+    const bool wide = (N % 4) == 0 && (reinterpret_cast<uintptr_t>(d_xspec) & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(d_auto0) | reinterpret_cast<uintptr_t>(d_auto1)) & 7) == 0;
+    dim3 grid(wide ? (N + 511) / 512 : (N + 255) / 256, 1);
     for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
         const long long nb = std::min<long long>(65535, n_blocks - b0);
         grid.y = (unsigned)nb;
+        if (wide)
+            fx::generic::finalize_rows2_kernel<<<grid, 256, 0, h->stream>>>(
+                h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)b0,
+                1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0, d_auto1);
+        else
         fx::generic::finalize_rows_kernel<<<grid, 256, 0, h->stream>>>(
             h->d_part_x, h->d_part_a, N, h->parts_per_block ? nullptr : h->d_plan + h->off_blk, (int)b0,
             1.0f / (float)h->P, h->rot_set ? h->d_rot : nullptr, reinterpret_cast<float2 *>(d_xspec), d_auto0, d_auto1);
