@@ -46,7 +46,7 @@ if os.path.exists(lc):
         d[L["name"]].append(L)
     tot = sum(L["time"] for L in launches.values())
     # one step of bench.py --profile = byte sums + fused + finalize: traffic of a step = sum of the means
-    step_names = [k for k in d if any(t in k for t in ("block_sums_kernel", "fused_kernel_stag", "finalize_rows_kernel"))]
+    step_names = [k for k in d if any(t in k for t in ("block_sums_kernel", "fused_kernel_stag", "finalize_rows"))]
     if step_names:
         step_dram = sum(sum(L["dram"] for L in d[k]) / len(d[k]) for k in step_names)
     with open(os.path.join(P, f"{rnd}{tag}_launches.csv"), "w") as fh:
