@@ -76,6 +76,7 @@ struct fx_handle {
         cudaEvent_t uploaded = nullptr;
         bool upload_recorded = false;
         unsigned long long last_use = 0;
+        unsigned long long gen = 0;               // bumped whenever the slot is rebuilt (captured graphs check it)
     };
     static constexpr int kPlanSlots = 4;
     PlanSlot plans[kPlanSlots];
@@ -106,8 +107,29 @@ struct fx_handle {
     float2 *d_lag_twH = nullptr;               // W_M^(n2*k1), [G][4096]
     float *d_pval = nullptr;
     long long *d_pidx = nullptr;
-    long long *d_lag_idx = nullptr;
+    long long *d_lag_idx = nullptr;            // {int64 imax; float nb[4]}: d_lag_nb points into it
     float *d_lag_nb = nullptr;
+    // fx_lag_* called again with the same device buffers (periodic re-calibration on a reused staging area) replays a
+    // CUDA graph of its ~10 launches: a launch-bound chain, 104 -> ~65 us per one-block call
+    struct LagGraph {
+        const void *d0 = nullptr, *d1 = nullptr;
+        long long nb = 0;
+        int u8 = 0;
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+        unsigned long long last_use = 0;
+        // what the captured launches point at: plan slots (index, generation) and the growable buffers
+        int n_plans = 0, plan_idx[4] = {0, 0, 0, 0};
+        unsigned long long plan_gen[4] = {0, 0, 0, 0};
+        const void *z = nullptr, *px = nullptr, *pa = nullptr;
+    };
+    LagGraph lag_graphs[2];
+    LagGraph *capture_into = nullptr;
+    unsigned long long lag_graph_clock = 0;
+    unsigned long long *d_lag_sums = nullptr;    // byte sums of the captured calls (their own, outside the pre-pass double buffer)
+    struct LagResult { long long idx; float nb[4]; };
+    LagResult *h_lag_res = nullptr;              // pinned
+    bool capturing = false, plan_built_in_capture = false;
 
     // host-pipeline staging (fx_process_host)
     uint8_t *d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
@@ -196,6 +218,20 @@ int drain_timed(fx_handle *h) {
 // ---- per-block byte sums for both channels --------------------------------
 int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long long n_blocks, long long S = 0) {
     if (S <= 0) S = h->cfg.num_samp;
+    if (h->capturing) {
+        // inside a stream capture (the lag search's graph): no second stream, no events, a buffer of its own
+        h->d_sums = h->d_lag_sums;
+        FX_CUDA(h, cudaMemsetAsync(h->d_sums, 0, sizeof(unsigned long long) * 4 * n_blocks, h->stream));
+        long long chunks = std::max<long long>(1, std::min<long long>(S / 8192, n_blocks >= 64 ? 64 : 4096 / n_blocks));
+        for (long long b0 = 0; b0 < n_blocks; b0 += 65535) {
+            const long long nb = std::min<long long>(65535, n_blocks - b0);
+            dim3 grid((unsigned)chunks, (unsigned)nb, 2);
+            fx::generic::block_sums_kernel<<<grid, 128, 0, h->stream>>>(d_iq0 + 2 * S * b0, d_iq1 + 2 * S * b0, S,
+                                                                        h->d_sums + 4 * b0, 4);
+            FX_LAUNCH_CHECK(h, "block_sums");
+        }
+        return FX_OK;
+    }
     const int set = (h->sums_idx ^= 1);
     h->d_sums = h->d_sums_set[set];
     cudaStream_t st = h->stream_aux;
@@ -219,6 +255,7 @@ int launch_sums(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, long l
 }
 // call after the last kernel that reads h->d_sums has been enqueued on h->stream
 int release_sums(fx_handle *h) {
+    if (h->capturing) return FX_OK;
     const int set = h->sums_idx;
     FX_CUDA(h, cudaEventRecord(h->ev_sums_free[set], h->stream));
     h->sums_free_recorded[set] = true;
@@ -251,6 +288,7 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0, int logF = 
     for (auto &pl : h->plans)
         if (pl.units == n_blocks && pl.P == P && pl.logF == logF && pl.min_fpc == min_fpc) slot = &pl;
     if (!slot) {
+        if (h->capturing) h->plan_built_in_capture = true;      // the upload would be replayed from a buffer that moves on
         slot = &h->plans[0];
         for (auto &pl : h->plans)
             if (pl.last_use < slot->last_use) slot = &pl;
@@ -295,12 +333,22 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0, int logF = 
         slot->P = P;
         slot->logF = logF;
         slot->min_fpc = min_fpc;
+        slot->gen++;
         // stream-ordered: kernels already queued with this slot's old plan finish before the copy lands
         FX_CUDA(h, cudaMemcpyAsync(slot->d_plan, flat, n_int * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         FX_CUDA(h, cudaEventRecord(slot->uploaded, h->stream));
         slot->upload_recorded = true;
     }
     slot->last_use = ++h->plan_clock;
+    if (h->capturing && h->capture_into) {
+        auto *g = h->capture_into;
+        if (g->n_plans < 4) {
+            g->plan_idx[g->n_plans] = (int)(slot - h->plans);
+            g->plan_gen[g->n_plans] = slot->gen;
+            g->n_plans++;
+        } else
+            h->plan_built_in_capture = true;       // more plans than the record holds: do not keep the graph
+    }
     h->d_plan = slot->d_plan;
     h->off_cta = slot->off_cta;
     h->off_blk = slot->off_blk;
@@ -1086,8 +1134,12 @@ int ensure_lag(fx_handle *h, long long M) {
     if (!h->d_pval) {
         FX_CUDA(h, cudaMalloc(&h->d_pval, sizeof(float) * 1024));
         FX_CUDA(h, cudaMalloc(&h->d_pidx, sizeof(long long) * 1024));
-        FX_CUDA(h, cudaMalloc(&h->d_lag_idx, sizeof(long long)));
-        FX_CUDA(h, cudaMalloc(&h->d_lag_nb, sizeof(float) * 4));
+        // one result record {int64 imax; float nb[4]}: one D2H copy fetches it
+        FX_CUDA(h, cudaMalloc(&h->d_lag_idx, 32));
+        FX_CUDA(h, cudaMemset(h->d_lag_idx, 0, 32));
+        h->d_lag_nb = reinterpret_cast<float *>(h->d_lag_idx + 1);
+        FX_CUDA(h, cudaMalloc(&h->d_lag_sums, sizeof(unsigned long long) * 4 * (size_t)h->cfg.max_blocks));
+        FX_CUDA(h, cudaHostAlloc(&h->h_lag_res, sizeof(fx_handle::LagResult), cudaHostAllocDefault));
     }
     h->lagM = M;
     return FX_OK;
@@ -1244,15 +1296,32 @@ int lag_finish_device(fx_handle *h, const float2 *d_xacc) {
     return FX_OK;
 }
 
-int lag_fetch(fx_handle *h, int64_t *imax, float nbhd[3]) {
-    long long idx = 0;
-    float nb[3];
-    FX_CUDA(h, cudaMemcpyAsync(&idx, h->d_lag_idx, sizeof(idx), cudaMemcpyDeviceToHost, h->stream));
-    FX_CUDA(h, cudaMemcpyAsync(nb, h->d_lag_nb, sizeof(nb), cudaMemcpyDeviceToHost, h->stream));
-    FX_CUDA(h, cudaStreamSynchronize(h->stream));
-    *imax = idx;
-    nbhd[0] = nb[0]; nbhd[1] = nb[1]; nbhd[2] = nb[2];
+// results of lag_finish_device -> the handle's pinned result buffer (asynchronous; also a node of the lag graph)
+int lag_fetch_enqueue(fx_handle *h) {
+    FX_CUDA(h, cudaMemcpyAsync(h->h_lag_res, h->d_lag_idx, sizeof(fx_handle::LagResult), cudaMemcpyDeviceToHost, h->stream));
     return FX_OK;
+}
+int lag_fetch(fx_handle *h, int64_t *imax, float nbhd[3]) {
+    int rc = lag_fetch_enqueue(h);
+    if (rc) return rc;
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *imax = h->h_lag_res->idx;
+    nbhd[0] = h->h_lag_res->nb[0]; nbhd[1] = h->h_lag_res->nb[1]; nbhd[2] = h->h_lag_res->nb[2];
+    return FX_OK;
+}
+
+bool lag_graphs_enabled() {
+    static bool v = [] { const char *e = getenv("EFFEX_FX_LAG_GRAPH"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
+template <bool U8>
+int lag_enqueue(fx_handle *h, const void *d0, const void *d1, long long n_blocks) {
+    int rc = lag_accumulate_impl<U8>(h, d0, d1, n_blocks, h->d_lag_acc, 1);
+    if (rc) return rc;
+    rc = lag_finish_device(h, h->d_lag_acc);
+    if (rc) return rc;
+    return lag_fetch_enqueue(h);
 }
 
 template <bool U8>
@@ -1260,17 +1329,79 @@ int lag_impl(fx_handle *h, const void *d0, const void *d1, long long n_blocks, i
     if (!h) return FX_ERR_INVALID;
     if (!d0 || !d1 || !imax || !nbhd) return fail(h, FX_ERR_INVALID, "null pointer");
     if (n_blocks < 1) return fail(h, FX_ERR_INVALID, "n_blocks must be >= 1");
+    if (U8 && n_blocks > h->cfg.max_blocks) return fail(h, FX_ERR_INVALID, "n_blocks exceeds max_blocks");
     FX_CUDA(h, cudaSetDevice(h->cfg.device));
     const long long n = h->cfg.num_samp;
     long long M = 2;
     while (M < 2 * n) M <<= 1;
     int rc = ensure_lag(h, M);
     if (rc) return rc;
-    rc = lag_accumulate_impl<U8>(h, d0, d1, n_blocks, h->d_lag_acc, 1);
-    if (rc) return rc;
-    rc = lag_finish_device(h, h->d_lag_acc);
-    if (rc) return rc;
-    return lag_fetch(h, imax, nbhd);
+    // The chain is launch-bound (byte sums, head, tail, fold, inverse head and tail, two argmax stages, two copies).
+    // A call that repeats the previous one's buffers and block count replays a graph captured on its SECOND
+    // occurrence (by then every buffer and plan the chain needs exists: nothing allocates or uploads inside the capture).
+    fx_handle::LagGraph *slot = nullptr;
+    if (h->lag_fast && !h->timing && lag_graphs_enabled() && h->h_lag_res) {
+        for (auto &g : h->lag_graphs)
+            if (g.d0 == d0 && g.d1 == d1 && g.nb == n_blocks && g.u8 == (U8 ? 1 : 0)) slot = &g;
+        if (!slot) {                                   // first occurrence: remember it, run it launch by launch
+            slot = &h->lag_graphs[0];
+            for (auto &g : h->lag_graphs)
+                if (g.last_use < slot->last_use) slot = &g;
+            if (slot->exec) cudaGraphExecDestroy(slot->exec);
+            *slot = fx_handle::LagGraph();
+            slot->d0 = d0; slot->d1 = d1; slot->nb = n_blocks; slot->u8 = U8 ? 1 : 0;
+            slot->last_use = ++h->lag_graph_clock;
+            slot = nullptr;
+        } else {
+            slot->last_use = ++h->lag_graph_clock;
+            if (slot->exec) {                          // do the captured launches still point at live plans and buffers?
+                bool live = slot->z == h->d_lag_z && slot->px == h->d_part_x && slot->pa == h->d_part_a;
+                for (int i = 0; i < slot->n_plans; ++i) live = live && h->plans[slot->plan_idx[i]].gen == slot->plan_gen[i];
+                if (!live) {
+                    cudaGraphExecDestroy(slot->exec);
+                    slot->exec = nullptr;
+                }
+            }
+            if (!slot->exec) {
+                slot->n_plans = 0;
+                h->capture_into = slot;
+                const long long launches0 = h->launches;
+                unsigned long long *sums0 = h->d_sums;
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    h->capturing = true;
+                    h->plan_built_in_capture = false;
+                    const int crc = lag_enqueue<U8>(h, d0, d1, n_blocks);
+                    h->capturing = false;
+                    h->d_sums = sums0;
+                    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+                    const long long captured = h->launches - launches0;
+                    h->launches = launches0;
+                    if (crc == FX_OK && e == cudaSuccess && graph && !h->plan_built_in_capture &&
+                        cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess) {
+                        slot->launches = captured;
+                        slot->z = h->d_lag_z; slot->px = h->d_part_x; slot->pa = h->d_part_a;
+                    } else
+                        slot->exec = nullptr;
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();                // a failed capture leaves a sticky-free error behind
+                }
+                h->capture_into = nullptr;
+            }
+            if (!slot->exec) slot = nullptr;
+        }
+    }
+    if (slot) {
+        FX_CUDA(h, cudaGraphLaunch(slot->exec, h->stream));
+        h->launches += slot->launches;
+    } else {
+        rc = lag_enqueue<U8>(h, d0, d1, n_blocks);
+        if (rc) return rc;
+    }
+    FX_CUDA(h, cudaStreamSynchronize(h->stream));
+    *imax = h->h_lag_res->idx;
+    nbhd[0] = h->h_lag_res->nb[0]; nbhd[1] = h->h_lag_res->nb[1]; nbhd[2] = h->h_lag_res->nb[2];
+    return FX_OK;
 }
 
 // tables of the staggered / tail kernels in stage-A/B REGISTER order, two registers per float4 (one LDS.128):
@@ -1567,10 +1698,13 @@ int fx_destroy(fx_handle *h) {
     for (auto &ep : h->evs) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
     void *ptrs[] = {h->d_taps_u8, h->d_taps_c, h->d_taps4, h->d_twA, h->d_twB, h->d_twAp, h->d_twBp, h->d_rot, h->d_sums_set[0], h->d_sums_set[1], h->d_part_x,
                     h->d_part_a, h->d_int_scratch, h->d_tile_counters, h->d_lag_z, h->d_lag_twAp, h->d_lag_twBp, h->d_lag_twH, h->d_bs_chirp, h->d_bs_B, h->d_bs_a, h->d_bs_tmp, h->d_z, h->d_twH, h->d_halo_pad[0], h->d_halo_pad[1], h->d_halo_big[0], h->d_halo_big[1], h->d_g0, h->d_g1, h->d_gtmp, h->d_lag_rows, h->d_lag_tmp, h->d_lag_acc,
-                    h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_lag_nb, h->d_in[0][0], h->d_in[0][1],
+                    h->d_lag_acc_tmp, h->d_pval, h->d_pidx, h->d_lag_idx, h->d_in[0][0], h->d_in[0][1],
                     h->d_in[1][0], h->d_in[1][1], h->d_out_x[0], h->d_out_x[1], h->d_out_a0[0], h->d_out_a0[1],
                     h->d_out_a1[0], h->d_out_a1[1]};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &g : h->lag_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->d_lag_sums) cudaFree(h->d_lag_sums);
+    if (h->h_lag_res) cudaFreeHost(h->h_lag_res);
     for (auto &pl : h->plans) {
         if (pl.d_plan) cudaFree(pl.d_plan);
         if (pl.h_pin) cudaFreeHost(pl.h_pin);

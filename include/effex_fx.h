@@ -197,7 +197,12 @@ int fx_pfb_u8(fx_handle *h, const uint8_t *d_iq, float *d_frames);
  * With n_blocks > 1 the 2n-point cross-spectrum is accumulated over the
  * blocks before the single inverse FFT (BASELINE config 2).  Synchronous.
  * Integer lag = n - imax.  nbhd[k] = -1 marks an out-of-range neighbour
- * (the reference raises IndexError there, effex.py:619 TODO).                */
+ * (the reference raises IndexError there, effex.py:619 TODO).
+ * The chain is ~10 short launches; a call that repeats the previous call's
+ * device buffers and n_blocks (re-calibration on a reused staging area) is
+ * captured into a CUDA graph on its second occurrence and replayed from the
+ * third on -- the replay reads the buffers' current contents
+ * (EFFEX_FX_LAG_GRAPH=0 disables this).                                      */
 int fx_lag_c64(fx_handle *h, const float *d_x0, const float *d_x1, int64_t n_blocks,
                int64_t *imax, float nbhd[3]);
 int fx_lag_u8(fx_handle *h, const uint8_t *d_iq0, const uint8_t *d_iq1, int64_t n_blocks,

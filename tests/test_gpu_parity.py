@@ -498,3 +498,32 @@ def test_big_nbins_unaligned_input_and_ragged_num_samp():
         for b in range(nb):
             assert_close(x[b], ref[b], what=f"S={S} shift={shift} block {b} vs oracle")
         eng.close()
+
+
+def test_lag_graph_replay_follows_the_data_and_survives_plan_eviction():
+    """fx_lag_u8 replays a CUDA graph when it is called again with the same buffers: the replay must read the buffers'
+    CURRENT contents, and must be dropped when other calls have recycled the segment plans its launches point at."""
+    S, N, nb = 2**16, 4096, 6
+    eng = FxEngine(S, N, 4, max_blocks=nb)
+    raws = {d: synth.correlated_pair(nb * S, delay=d, seed=40 + d) for d in (11, -23)}
+    d0, d1 = dev(raws[11][0]).clone(), dev(raws[11][1]).clone()
+    for _ in range(4):                                   # launch by launch, capture, replay, replay
+        r = eng.lag(d0, d1, 2)
+        assert r[0] - r[1] == 11
+    first = r
+    d0.copy_(dev(raws[-23][0])); d1.copy_(dev(raws[-23][1]))      # same buffers, new contents
+    r = eng.lag(d0, d1, 2)
+    assert r[0] - r[1] == -23
+    for k in range(1, nb + 1):                           # six other shapes through the 4-slot plan cache
+        eng.process(d0, d1, k)
+    r = eng.lag(d0, d1, 2)
+    assert r[0] - r[1] == -23
+    d0.copy_(dev(raws[11][0])); d1.copy_(dev(raws[11][1]))
+    for _ in range(3):
+        r = eng.lag(d0, d1, 2)
+        assert r[:2] == first[:2]
+        np.testing.assert_allclose(r[2:], first[2:], rtol=1e-6)
+    # a different block count on the same buffers is a different graph
+    r1 = eng.lag(d0, d1, 1)
+    assert r1[0] - r1[1] == 11
+    eng.close()
