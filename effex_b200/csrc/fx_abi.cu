@@ -265,6 +265,7 @@ int release_sums(fx_handle *h) {
 int ensure_parts(fx_handle *h, size_t n_segs, size_t bins_per_seg = 0) {
     const size_t elems = n_segs * (bins_per_seg ? bins_per_seg : (size_t)h->cfg.nbins);
     if (elems <= h->part_cap) return FX_OK;
+    if (h->capturing) return fail(h, FX_ERR_STATE, "partial-sum buffers would grow during a stream capture");
     if (h->d_part_x) cudaFree(h->d_part_x);
     if (h->d_part_a) cudaFree(h->d_part_a);
     h->d_part_x = h->d_part_a = nullptr;
@@ -288,7 +289,12 @@ int plan_segments(fx_handle *h, long long n_blocks, long long P = 0, int logF = 
     for (auto &pl : h->plans)
         if (pl.units == n_blocks && pl.P == P && pl.logF == logF && pl.min_fpc == min_fpc) slot = &pl;
     if (!slot) {
-        if (h->capturing) h->plan_built_in_capture = true;      // the upload would be replayed from a buffer that moves on
+        if (h->capturing) {
+            // a capture only records: the upload would not happen now, and a replay would copy from a staging buffer that
+            // has moved on.  Refuse before anything is touched; the caller drops the capture and runs launch by launch.
+            h->plan_built_in_capture = true;
+            return fail(h, FX_ERR_STATE, "segment plan not resident during a stream capture");
+        }
         slot = &h->plans[0];
         for (auto &pl : h->plans)
             if (pl.last_use < slot->last_use) slot = &pl;
@@ -1147,6 +1153,7 @@ int ensure_lag(fx_handle *h, long long M) {
 
 int ensure_lag_z(fx_handle *h, size_t elems) {
     if (elems <= h->lag_z_cap) return FX_OK;
+    if (h->capturing) return fail(h, FX_ERR_STATE, "Z would grow during a stream capture");
     if (h->d_lag_z) cudaFree(h->d_lag_z);
     h->d_lag_z = nullptr;
     h->lag_z_cap = 0;
